@@ -1,0 +1,120 @@
+/*
+ * kissmcmc_cuda.h -- C-ABI of libkissmcmc_cuda.so, the B200 (sm_100a) implementation of
+ * KissMCMC.jl's emcee stretch-move hot path.
+ *
+ * The reference (KissMCMC.jl v0.2.2) has no FFI: its boundary is three exported Julia
+ * functions (src/KissMCMC.jl:8) and the call pdf(theta) to a user closure
+ * (src/samplers.jl:257, :209, :334-336).  This header is the interface a
+ * `KissMCMC.CUDABackend` Julia module binds with `ccall` and that the
+ * Python host mirror (kissmcmc.jl_b200/) binds with ctypes.  Each entry point cites the
+ * reference code it replaces.
+ *
+ * Conventions
+ *   - every function returns int32 status, 0 = ok; kmc_last_error() returns a thread-local
+ *     message for the last non-zero status.  No exceptions, no callbacks into the host.
+ *   - plain pointers and sizes only.  The CALLER owns every host buffer and must keep it
+ *     alive for the duration of the call (Julia: GC.@preserve).
+ *   - opaque handles own all device memory.  A sampler handle is used by one host thread at a
+ *     time.
+ *   - walker arrays cross the ABI as dense FP64 `d x nw` column-major (Julia
+ *     `reduce(hcat, theta0s)`), which is C row-major [nw][d].  Chains come back as
+ *     `d x ns x nw` column-major = C [nw][ns][d] -- the (ntheta, nsamples, nchains) layout of
+ *     the reference's int_acorr (src/analysis.jl:143); log-densities as `ns x nw` = C [nw][ns].
+ *   - walker indices are 0-based across the ABI (the Julia wrapper subtracts 1).
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef KISSMCMC_CUDA_H
+#define KISSMCMC_CUDA_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMC_OK 0
+#define KMC_ERR_INVALID 1     /* bad argument (the reference's @assert, src/samplers.jl:200-205) */
+#define KMC_ERR_CUDA 2        /* CUDA runtime error or no device */
+#define KMC_ERR_UNSUPPORTED 3 /* density / dimension combination with no kernel */
+#define KMC_ERR_STATE 4       /* call not valid in the handle's current state */
+
+#define KMC_MODE_PHILOX 0 /* free-running, counter-based Philox4x32-10 draws */
+#define KMC_MODE_REPLAY 1 /* partner / z / u uploaded by the caller */
+
+typedef struct kmc_density_s *kmc_density_t;
+typedef struct kmc_sampler_s *kmc_sampler_t;
+
+typedef struct kmc_emcee_opts {
+    int64_t niter_walker;   /* niter / nwalkers    (src/samplers.jl:203) */
+    int64_t nburnin_walker; /* nburnin / nwalkers  (src/samplers.jl:204) */
+    int64_t nthin;          /* store every nthin-th iteration (:268) */
+    double a_scale;         /* stretch scale a > 1 (:200) */
+    uint64_t seed;          /* Philox key */
+    int32_t mode;           /* KMC_MODE_* */
+    int32_t device;         /* CUDA device ordinal */
+    int64_t walker_id_base; /* added to local walker indices in the Philox counter, so shards of
+                               one ensemble (or independent ensembles) draw distinct streams */
+    int32_t launch_mode;    /* 0 = persistent kernel, grid barrier between half-steps (default);
+                               1 = one launch per half-step */
+    int32_t reserved;
+} kmc_emcee_opts;
+
+/* Library / device ------------------------------------------------------------------- */
+int32_t kmc_version(void);
+const char *kmc_last_error(void);
+int32_t kmc_device_count(int32_t *count);
+
+/* Log-density plugin registry: replaces the user closure `pdf` (src/samplers.jl:257,:209).
+ *   "exponential"  README.md:15             params: none
+ *   "rosenbrock"   test/runtests.jl:68      params: [a, b, T] (reference: 1, 100, 20), d = 2
+ *   "gaussian"     test/runtests.jl:53,61   params: [mu(d), A(d*d row-major), lognorm],
+ *                                           logp = lognorm - 0.5*|A (x-mu)|^2
+ *   "lognormal"    test/runtests.jl:56      params: [mu, sigma, log(sigma)+0.5*log(2pi)], d = 1
+ *   "logistic"     BASELINE.json config 4   params: [prior_sigma]; data: float32 X[N][d] then y[N]
+ * `data` may be NULL.  params/data are copied; the caller may free them on return. */
+int32_t kmc_density_create(const char *name, int32_t d, const double *params, int64_t nparams,
+                           const void *data, int64_t data_bytes, int32_t device,
+                           kmc_density_t *out);
+int32_t kmc_density_destroy(kmc_density_t h);
+/* Batched log-density of nw points (host in, host out).  Used for the initial p0s
+ * (src/samplers.jl:209-210) and by make_theta0s (:334-338). */
+int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, double *logp_out);
+
+/* Sampler: _emcee, src/samplers.jl:232-293 ------------------------------------------- */
+/* Uploads theta0s (never mutated, :198), checks the reference's asserts (:200-205: a_scale > 1,
+ * even nwalkers, nwalkers >= d + 2), evaluates the initial log-densities (:209) and allocates
+ * the thinned chain store (ns = (niter_walker - nburnin_walker) / nthin samples per walker). */
+int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t nwalkers,
+                         int32_t d, const kmc_emcee_opts *opts, kmc_sampler_t *out);
+int32_t kmc_emcee_destroy(kmc_sampler_t s);
+/* Launch on a caller-owned CUDA stream (a cudaStream_t passed as void*); NULL = the
+ * sampler's own stream. */
+int32_t kmc_emcee_set_stream(kmc_sampler_t s, void *cuda_stream);
+/* Replay mode: draws for `niters` outer iterations starting at the sampler's current
+ * iteration, each array of length niters*nwalkers indexed ((t*2 + batch)*(nwalkers/2) + i),
+ * i = position of the active walker in its half (:247-252,:260).  partner = global 0-based
+ * index of the passive walker, z = stretch factor, u = accept uniform. */
+int32_t kmc_emcee_set_replay(kmc_sampler_t s, const int64_t *partner, const double *z,
+                             const double *u, int64_t niters);
+/* Advance `niters` outer iterations (niters < 0: all that remain).  Asynchronous on the
+ * sampler's stream. */
+int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters);
+int32_t kmc_emcee_sync(kmc_sampler_t s);
+/* Device time of the kernels launched by the last kmc_emcee_run (CUDA events on the launch
+ * stream) and how many kernels that was.  Synchronises. */
+int32_t kmc_emcee_last_run_ms(kmc_sampler_t s, double *ms, int64_t *launches);
+/* Accept-counter statistics of the progress display (:276-278): mean, std (n-1) and number
+ * of walkers more than 2 std from the mean, reduced on the device.  Synchronises. */
+int32_t kmc_emcee_progress(kmc_sampler_t s, int64_t *iters_done, double *naccept_mean,
+                           double *naccept_std, int64_t *outliers);
+int32_t kmc_emcee_nsamples(kmc_sampler_t s, int64_t *ns);
+/* Results (:291-292).  thetas [nw][ns][d], logp [nw][ns], accept_ratio [nw]; any may be NULL. */
+int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp,
+                               double *accept_ratio);
+/* Current ensemble: theta [nw][d], logp [nw], naccept [nw]; any may be NULL. */
+int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KISSMCMC_CUDA_H */

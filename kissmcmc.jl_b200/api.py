@@ -1,0 +1,370 @@
+"""Host-side mirror of KissMCMC.jl's public emcee API over libkissmcmc_cuda.so.
+
+Drop-in names, argument meaning and error behaviour of the reference
+(/root/reference/src/samplers.jl):
+
+    emcee(logdensity, theta0s; niter, nburnin, nthin, a_scale, use_progress_meter, hasblob,
+          init_blobs, reduce_blob!)                               :188-216
+    make_theta0s(theta0, ball_radius, logdensity, nwalkers; ...)  :311-349
+    squash_walkers(thetas, accept_ratio, logdensities, blobs; ...) :372-428
+
+The one deliberate difference: `logdensity` is a device plugin descriptor (`LogDensity`) and
+not a closure -- user closures cannot cross the C-ABI onto the GPU and there is no CPU
+fallback.  `hasblob=True` raises (arbitrary host objects cannot live on the device).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import sys
+import time
+import warnings
+
+import numpy as np
+
+from . import _lib
+from ._lib import EmceeOpts, KmcError, MODE_PHILOX, MODE_REPLAY, check, lib
+
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+
+def _ptr(a, typ=_dp):
+    return a.ctypes.data_as(typ) if a is not None else None
+
+
+# ------------------------------------------------------------------------------------------
+# Log-density plugin registry (replaces the closure `pdf`, src/samplers.jl:257)
+
+class LogDensity:
+    """A device log-density plugin instance: name + parameters (+ optional data array)."""
+
+    def __init__(self, name: str, d: int, params=(), data: np.ndarray | None = None, device: int = 0):
+        self.name, self.d, self.device = name, int(d), int(device)
+        self.params = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+        self.data = None if data is None else np.ascontiguousarray(data)
+        h = C.c_void_p()
+        check(lib.kmc_density_create(
+            name.encode(), self.d, _ptr(self.params) if self.params.size else None, self.params.size,
+            self.data.ctypes.data_as(C.c_void_p) if self.data is not None else None,
+            self.data.nbytes if self.data is not None else 0, self.device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.kmc_density_destroy(h)
+
+    def __call__(self, theta):
+        """logdensity(theta) like the reference closure: one point -> float, [n,d] -> [n]."""
+        th = np.asarray(theta, dtype=np.float64)
+        single = th.ndim == 0 or (th.ndim == 1 and self.d > 1)  # for d == 1 a 1-D array is a batch
+        out = self.eval(th.reshape(-1, self.d))
+        return float(out[0]) if single else out
+
+    def eval(self, thetas) -> np.ndarray:
+        th = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(-1, self.d))
+        out = np.empty(th.shape[0])
+        check(lib.kmc_density_eval(self._h, _ptr(th), th.shape[0], _ptr(out)))
+        return out
+
+
+def exponential(d: int = 1, device: int = 0) -> LogDensity:
+    """README.md:15  logpdf(x) = x<0 ? -Inf : -x."""
+    return LogDensity("exponential", d, device=device)
+
+
+def rosenbrock(a: float = 1.0, b: float = 100.0, temper: float = 20.0, device: int = 0) -> LogDensity:
+    """test/runtests.jl:68  -(b*(x2-x1^2)^2 + (a-x1)^2)/temper."""
+    return LogDensity("rosenbrock", 2, [a, b, temper], device=device)
+
+
+def gaussian_params(mean, cov) -> np.ndarray:
+    """[mu, A row-major, lognorm] with A = chol(cov^-1)^T so that |A(x-mu)|^2 is the Mahalanobis form."""
+    mu = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    cov = np.atleast_2d(np.asarray(cov, dtype=np.float64))
+    d = mu.size
+    prec = np.linalg.inv(cov)
+    L = np.linalg.cholesky((prec + prec.T) / 2)  # prec = L L^T,  x^T prec x = |L^T x|^2
+    A = L.T
+    lognorm = float(np.sum(np.log(np.diag(L))) - 0.5 * d * math.log(2 * math.pi))
+    return np.concatenate([mu, A.ravel(), [lognorm]])
+
+
+def gaussian(mean, cov, device: int = 0) -> LogDensity:
+    """MvNormal(mean, cov) (test/runtests.jl:53,61); a scalar mean/variance gives Normal."""
+    mu = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    return LogDensity("gaussian", mu.size, gaussian_params(mean, cov), device=device)
+
+
+def lognormal(mu: float = 0.0, sigma: float = 1.0, device: int = 0) -> LogDensity:
+    """LogNormal(mu, sigma) (test/runtests.jl:56)."""
+    return LogDensity("lognormal", 1, [mu, sigma, math.log(sigma) + 0.5 * math.log(2 * math.pi)], device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# Low-level sampler handle
+
+class Sampler:
+    """Owns a kmc_sampler_t.  Counts are PER WALKER (niter_walker = niter // nwalkers)."""
+
+    def __init__(self, logdensity: LogDensity, theta0s, niter_walker, nburnin_walker, nthin=1, a_scale=2.0,
+                 seed=0, mode=MODE_PHILOX, device=None, walker_id_base=0, launch_mode=0):
+        x = np.ascontiguousarray(np.asarray(theta0s, dtype=np.float64))
+        if x.ndim == 1:
+            x = x.reshape(-1, 1)
+        self.nw, self.d = x.shape
+        self.logdensity = logdensity
+        self.opts = EmceeOpts(int(niter_walker), int(nburnin_walker), int(nthin), float(a_scale), int(seed),
+                              int(mode), int(logdensity.device if device is None else device),
+                              int(walker_id_base), int(launch_mode), 0)
+        h = C.c_void_p()
+        check(lib.kmc_emcee_create(logdensity._h, _ptr(x), self.nw, self.d, C.byref(self.opts), C.byref(h)))
+        self._h = h
+        n = C.c_int64()
+        check(lib.kmc_emcee_nsamples(h, C.byref(n)))
+        self.ns = n.value
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.kmc_emcee_destroy(h)
+
+    __del__ = close
+
+    def set_stream(self, cuda_stream: int | None):
+        check(lib.kmc_emcee_set_stream(self._h, C.c_void_p(cuda_stream or 0)))
+
+    def set_replay(self, partner, z, u):
+        p = np.ascontiguousarray(partner, dtype=np.int64)
+        z = np.ascontiguousarray(z, dtype=np.float64)
+        u = np.ascontiguousarray(u, dtype=np.float64)
+        if not (p.size == z.size == u.size) or p.size % self.nw:
+            raise ValueError("replay arrays must each hold niters*nwalkers draws")
+        check(lib.kmc_emcee_set_replay(self._h, _ptr(p, _i64p), _ptr(z), _ptr(u), p.size // self.nw))
+
+    def run(self, niters: int = -1, sync: bool = True):
+        check(lib.kmc_emcee_run(self._h, int(niters)))
+        if sync:
+            check(lib.kmc_emcee_sync(self._h))
+
+    def sync(self):
+        check(lib.kmc_emcee_sync(self._h))
+
+    def last_run_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        check(lib.kmc_emcee_last_run_ms(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def progress(self):
+        it, mean, sd, outl = C.c_int64(), C.c_double(), C.c_double(), C.c_int64()
+        check(lib.kmc_emcee_progress(self._h, C.byref(it), C.byref(mean), C.byref(sd), C.byref(outl)))
+        return it.value, mean.value, sd.value, outl.value
+
+    def results(self, out_thetas=None, out_logp=None, out_ratio=None):
+        th = np.empty((self.nw, self.ns, self.d)) if out_thetas is None else out_thetas
+        lp = np.empty((self.nw, self.ns)) if out_logp is None else out_logp
+        ar = np.empty(self.nw) if out_ratio is None else out_ratio
+        check(lib.kmc_emcee_copy_results(self._h, _ptr(th), _ptr(lp), _ptr(ar)))
+        return th, lp, ar
+
+    def state(self):
+        x, lp, na = np.empty((self.nw, self.d)), np.empty(self.nw), np.empty(self.nw, dtype=np.int64)
+        check(lib.kmc_emcee_copy_state(self._h, _ptr(x), _ptr(lp), _ptr(na, _i64p)))
+        return x, lp, na
+
+
+# ------------------------------------------------------------------------------------------
+# emcee  (src/samplers.jl:188-216)
+
+def _require_plugin(logdensity):
+    if not isinstance(logdensity, LogDensity):
+        raise TypeError(
+            "the CUDA backend takes a LogDensity plugin descriptor (exponential(), rosenbrock(), gaussian(), "
+            "lognormal(), ...) in place of a closure: user code cannot run on the device and there is no CPU "
+            "fallback")
+
+
+def emcee(logdensity, theta0s, *, niter=10**5, nburnin=None, nthin=1, a_scale=2.0, use_progress_meter=True,
+          hasblob=False, init_blobs=None, reduce_blob=None, seed=0, replay=None, launch_mode=0):
+    """The affine-invariant ensemble sampler; same call shape and 4-tuple as the reference.
+
+    Returns (thetas, accept_ratio, logdensities, None): thetas[w] is walker w's chain
+    ([nw, ns] for scalar theta, [nw, ns, d] otherwise), accept_ratio [nw], logdensities [nw, ns],
+    ns = ((niter // nw) - (nburnin // nw)) // nthin.  niter/nburnin are TOTAL walker-steps (:203-204).
+    `seed` keys the Philox draws; `replay=(partner, z, u)` uploads the draws instead.
+    """
+    _require_plugin(logdensity)
+    if hasblob or init_blobs is not None or reduce_blob is not None:
+        raise NotImplementedError("hasblob=True is not supported by the CUDA backend: blobs are arbitrary host "
+                                  "objects (src/samplers.jl:194-196)")
+    th = np.asarray(theta0s, dtype=np.float64)  # np.asarray + ascontiguousarray below = the deepcopy at :198
+    scalar_theta = th.ndim == 1
+    if nburnin is None:
+        nburnin = niter // 2                    # :190
+    assert a_scale > 1                          # :200
+    nwalkers = len(th)                          # :201
+    assert nwalkers % 2 == 0, "Use an even number of walkers."    # :202
+    niter_walker = niter // nwalkers            # :203
+    nburnin_walker = nburnin // nwalkers        # :204
+    npar = 1 if scalar_theta else th.shape[1]
+    assert nwalkers >= npar + 2, "Use more walkers: at least DOF+2, but better many more."  # :205
+
+    mode = MODE_REPLAY if replay is not None else MODE_PHILOX
+    s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, mode,
+                launch_mode=launch_mode)
+    try:
+        if replay is not None:
+            s.set_replay(*replay)
+        if use_progress_meter and niter_walker > 0:     # :213, :275-284 -- coarse, never per iteration
+            chunks = min(20, niter_walker)
+            done, t0 = 0, time.time()
+            for c in range(chunks):
+                upto = (niter_walker * (c + 1)) // chunks
+                s.run(upto - done)
+                done = upto
+                it, mean, sd, outl = s.progress()
+                nn = max(1, it - nburnin_walker if it > nburnin_walker else it)
+                sys.stderr.write(
+                    f"\remcee, niter={niter}, nwalkers={nwalkers}: {100 * done // niter_walker:3d}%  "
+                    f"accept_ratio_mean={mean / nn:.3g} accept_ratio_std={sd / nn:.3g} "
+                    f"accept_ratio_outliers={outl} burnin_phase={it <= nburnin_walker} "
+                    f"[{time.time() - t0:.1f}s]")
+            sys.stderr.write("\n")
+        else:
+            s.run(-1)
+        thetas, logp, ratio = s.results()
+    finally:
+        s.close()
+    if scalar_theta:
+        thetas = thetas[:, :, 0]
+    return thetas, ratio, logp, None
+
+
+# ------------------------------------------------------------------------------------------
+# make_theta0s  (src/samplers.jl:311-349)
+
+_M0, _M1, _W0, _W1 = 0xD2511F53, 0xCD9E8D57, 0x9E3779B9, 0xBB67AE85
+
+
+def philox4x32_10(c0, c1, c2, c3, k0, k1):
+    """Vectorised Philox4x32-10 (numpy uint64 lanes holding 32-bit words)."""
+    c0, c1, c2, c3 = (np.asarray(v, dtype=np.uint64) & np.uint64(0xFFFFFFFF) for v in (c0, c1, c2, c3))
+    c0, c1, c2, c3 = np.broadcast_arrays(c0, c1, c2, c3)
+    k0, k1 = int(k0) & 0xFFFFFFFF, int(k1) & 0xFFFFFFFF
+    mask, sh = np.uint64(0xFFFFFFFF), np.uint64(32)
+    for _ in range(10):
+        p0 = np.uint64(_M0) * c0
+        p1 = np.uint64(_M1) * c2
+        n0 = (p1 >> sh) ^ c1 ^ np.uint64(k0)
+        n2 = (p0 >> sh) ^ c3 ^ np.uint64(k1)
+        c0, c1, c2, c3 = n0, p1 & mask, n2, p0 & mask
+        k0, k1 = (k0 + _W0) & 0xFFFFFFFF, (k1 + _W1) & 0xFFFFFFFF
+    return c0, c1, c2, c3
+
+
+def ball_randn(seed: int, walkers, k: int, j: int, d: int) -> np.ndarray:
+    """Counter-based standard normals for make_theta0s: [len(walkers), d], a pure function of
+    (seed, walker, halving step k, try j, component).  Philox words -> two 32-bit uniforms in
+    (0,1] / [0,1) -> Box-Muller.  Stream tag 0x4D54 keeps it apart from the sampler's draws."""
+    w = np.atleast_1d(np.asarray(walkers, dtype=np.uint64))
+    comp = np.arange((d + 1) // 2, dtype=np.uint64)
+    r0, r1, r2, r3 = philox4x32_10(w[:, None], comp[None, :], np.uint64(k) << np.uint64(16) | np.uint64(j),
+                                   np.uint64(0x4D540000), seed, seed >> 32)
+    u1 = (r0.astype(np.float64) + 1.0) * 2.0 ** -32
+    u2 = r1.astype(np.float64) * 2.0 ** -32
+    rad = np.sqrt(-2.0 * np.log(u1))
+    z = np.stack([rad * np.cos(2 * np.pi * u2), rad * np.sin(2 * np.pi * u2)], axis=-1).reshape(len(w), -1)
+    return z[:, :d]
+
+
+def make_theta0s(theta0, ball_radius, logdensity, nwalkers, *, ball_radius_halfing_steps=7, ntries=100,
+                 hasblob=False, seed=0, randn=None):
+    """Initial ensemble inside a Gaussian ball around theta0, rejecting points of zero density.
+
+    Same loop semantics as the reference, including its quirks (cumulative, never-reset radius
+    halving at :326; a walker that exhausts every try is skipped, :344-345 cannot fire), but the
+    density calls are batched through the device plugin: all pending walkers are tried at once
+    and the sequential order is only replayed for the rare walker that needs a smaller ball.
+    randn(walkers, k, j) -> [len(walkers), d] normals (default: counter-based ball_randn).
+    Scalar theta0 -> array [nwalkers]; vector theta0 -> [nwalkers, d].
+    """
+    _require_plugin(logdensity)
+    if hasblob:
+        raise NotImplementedError("hasblob=True is not supported by the CUDA backend")
+    scalar = np.ndim(theta0) == 0
+    th0 = np.atleast_1d(np.asarray(theta0, dtype=np.float64))
+    npara = th0.size                                         # :315
+    br = np.asarray(ball_radius, dtype=np.float64)
+    br = np.ones(npara) * br if br.ndim == 0 else br.copy()  # :316-318
+    assert br.size == npara                                  # :319
+    if randn is None:
+        randn = lambda w, k, j: ball_randn(seed, w, k, j, npara)
+
+    out = np.empty((nwalkers, npara))
+    found = np.zeros(nwalkers, dtype=bool)
+    i0 = 0
+    while i0 < nwalkers:
+        pend = np.arange(i0, nwalkers)
+        for j in range(1, ntries + 1):                       # k = 1: radius factor 1/2^0 = 1
+            tmp = th0[None, :] + randn(pend, 1, j) * br[None, :]
+            ok = logdensity.eval(tmp) > -np.inf              # :338
+            out[pend[ok]] = tmp[ok]
+            found[pend[ok]] = True
+            pend = pend[~ok]
+            if pend.size == 0:
+                break
+        if pend.size == 0:
+            break
+        f = int(pend[0])            # first walker whose k=1 tries all failed: later ones must be redone
+        found[f + 1:] = False
+        for k in range(2, ball_radius_halfing_steps + 1):    # :324
+            br = br * (1.0 / 2.0 ** (k - 1))                 # :326 (cumulative, never reset)
+            for j in range(1, ntries + 1):
+                tmp = th0[None, :] + randn(np.array([f]), k, j) * br[None, :]
+                if logdensity.eval(tmp)[0] > -np.inf:
+                    out[f] = tmp[0]
+                    found[f] = True
+                    break
+            if found[f]:
+                break
+        i0 = f + 1
+    if not found.all():
+        warnings.warn("make_theta0s: could not find a point of non-zero density for "
+                      f"{int((~found).sum())} walker(s); like the reference they are silently skipped")
+    res = out[found]
+    return res[:, 0] if scalar else res
+
+
+# ------------------------------------------------------------------------------------------
+# squash_walkers  (src/samplers.jl:372-428)
+
+def squash_walkers(thetas, accept_ratio, logdensities=None, blobs=None, *, drop_low_accept_ratio=False,
+                   drop_fact=2, verbose=True, order=False, merge_blobs=None):
+    """Puts the samples of all walkers into one array (walker-major; time-major if order=True).
+
+    Returns (thetas, mean(accept_ratio[kept]), logdensities | None, None)."""
+    if blobs is not None:
+        raise NotImplementedError("blobs are not supported by the CUDA backend")
+    thetas = np.asarray(thetas)
+    accept_ratio = np.asarray(accept_ratio, dtype=np.float64)
+    nwalkers = len(accept_ratio)                                             # :378
+    if drop_low_accept_ratio:                                                # :379-393
+        ma, sa = np.median(accept_ratio), np.std(accept_ratio, ddof=1)
+        if verbose:
+            print(f"Median accept ratio is {ma}, standard deviation is {sa}\n")
+        drop = accept_ratio <= ma - drop_fact * sa
+        if verbose:
+            for nc in np.nonzero(drop)[0]:
+                print(f"Dropping walker {nc + 1} with low accept ratio {accept_ratio[nc]}")
+        keep = np.nonzero(~drop)[0]
+    else:
+        keep = np.arange(nwalkers)                                           # :395
+    t = thetas[keep]
+    l = None if logdensities is None else np.asarray(logdensities)[keep]
+    if order:   # :415-426 stable sortperm of (1:ns repeated) == time-major, walkers in kept order
+        t = np.swapaxes(t, 0, 1)
+        l = None if l is None else np.swapaxes(l, 0, 1)
+    t = t.reshape((-1,) + thetas.shape[2:])                                  # :398-399
+    l = None if l is None else l.reshape(-1)
+    return t, float(np.mean(accept_ratio[keep])), l, None                    # :427

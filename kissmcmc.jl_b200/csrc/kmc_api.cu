@@ -1,0 +1,525 @@
+// kmc_api.cu -- C-ABI of libkissmcmc_cuda.so (see include/kissmcmc_cuda.h).
+//
+// Host-side runtime of the emcee hot path: handle management, argument checks that mirror
+// the reference's asserts (src/samplers.jl:200-205), kernel dispatch over the log-density
+// plugin registry, the thinned chain store and result copy-out.  No CPU fallback exists:
+// every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/kissmcmc_cuda.h"
+#include "kmc_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int32_t fail(int32_t code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                            \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(KMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
+                        __FILE__, __LINE__);                                                    \
+    } while (0)
+
+// ------------------------------------------------------------------ kernel registry
+struct Ops {
+    const void *run[2] = {nullptr, nullptr};  // [replay]
+    const void *eval = nullptr;
+    size_t dn_bytes = 0;
+    int nparams = 0;
+};
+
+template <template <int> class Dn, int D>
+Ops make_ops() {
+    Ops o;
+    o.run[0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
+    o.run[1] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
+    o.eval = (const void *)kmc::density_eval_kernel<Dn, D>;
+    o.dn_bytes = sizeof(Dn<D>);
+    o.nparams = Dn<D>::nparams;
+    return o;
+}
+
+template <template <int> class Dn>
+bool ops_for_dim(int d, Ops &o) {
+    switch (d) {
+        case 1: o = make_ops<Dn, 1>(); return true;
+        case 2: o = make_ops<Dn, 2>(); return true;
+        case 3: o = make_ops<Dn, 3>(); return true;
+        case 4: o = make_ops<Dn, 4>(); return true;
+        case 5: o = make_ops<Dn, 5>(); return true;
+        case 6: o = make_ops<Dn, 6>(); return true;
+        case 8: o = make_ops<Dn, 8>(); return true;
+        case 10: o = make_ops<Dn, 10>(); return true;
+        case 12: o = make_ops<Dn, 12>(); return true;
+        case 16: o = make_ops<Dn, 16>(); return true;
+        default: return false;
+    }
+}
+
+bool find_ops(int kind, int d, Ops &o) {
+    switch (kind) {
+        case kmc::KIND_EXPONENTIAL: return ops_for_dim<kmc::Exponential>(d, o);
+        case kmc::KIND_GAUSSIAN: return ops_for_dim<kmc::Gaussian>(d, o);
+        case kmc::KIND_ROSENBROCK:
+            if (d != 2) return false;
+            o = make_ops<kmc::Rosenbrock, 2>();
+            return true;
+        case kmc::KIND_LOGNORMAL:
+            if (d != 1) return false;
+            o = make_ops<kmc::LogNormal, 1>();
+            return true;
+        default: return false;
+    }
+}
+
+int kind_of(const char *name) {
+    if (!name) return -1;
+    if (!strcmp(name, "exponential")) return kmc::KIND_EXPONENTIAL;
+    if (!strcmp(name, "rosenbrock")) return kmc::KIND_ROSENBROCK;
+    if (!strcmp(name, "gaussian")) return kmc::KIND_GAUSSIAN;
+    if (!strcmp(name, "lognormal")) return kmc::KIND_LOGNORMAL;
+    if (!strcmp(name, "logistic")) return kmc::KIND_LOGISTIC;
+    return -1;
+}
+
+}  // namespace
+
+struct kmc_density_s {
+    int kind = -1;
+    int d = 0;
+    int device = 0;
+    std::vector<double> params;  // also the by-value kernel argument (padded to >= 1 double)
+    Ops ops;
+};
+
+struct kmc_sampler_s {
+    kmc_density_s *dn = nullptr;
+    kmc_emcee_opts opts{};
+    long long nw = 0, nhalf = 0, ns = 0;
+    int d = 0;
+    long long iters_done = 0;  // outer iterations completed (t)
+    double *x = nullptr, *lp = nullptr, *chain_x = nullptr, *chain_lp = nullptr;
+    unsigned *nacc = nullptr;
+    unsigned long long *barrier = nullptr;
+    unsigned long long bar_base = 0;
+    long long *rp_partner = nullptr;
+    double *rp_z = nullptr, *rp_u = nullptr;
+    long long rp_t0 = 0, rp_niters = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long last_launches = 0;
+    int max_blocks[2] = {0, 0};  // co-resident CTAs of run[replay]
+    unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
+};
+
+extern "C" {
+
+int32_t kmc_version(void) { return 100; }
+
+const char *kmc_last_error(void) { return g_err.c_str(); }
+
+int32_t kmc_device_count(int32_t *count) {
+    if (!count) return fail(KMC_ERR_INVALID, "count is NULL");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(KMC_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return KMC_OK;
+}
+
+int32_t kmc_density_create(const char *name, int32_t d, const double *params, int64_t nparams,
+                           const void *data, int64_t data_bytes, int32_t device,
+                           kmc_density_t *out) {
+    if (!out) return fail(KMC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    const int kind = kind_of(name);
+    if (kind < 0) return fail(KMC_ERR_INVALID, "unknown log-density plugin '%s'", name ? name : "(null)");
+    if (d < 1) return fail(KMC_ERR_INVALID, "d must be >= 1");
+    if (nparams < 0 || (nparams > 0 && !params)) return fail(KMC_ERR_INVALID, "bad params");
+    (void)data;
+    (void)data_bytes;
+    Ops ops;
+    if (!find_ops(kind, d, ops))
+        return fail(KMC_ERR_UNSUPPORTED, "no sm_100a kernel for plugin '%s' with d=%d", name, d);
+    if (nparams != ops.nparams)
+        return fail(KMC_ERR_INVALID, "plugin '%s' with d=%d takes %d parameters, got %lld", name, d,
+                    ops.nparams, (long long)nparams);
+    auto *h = new kmc_density_s;
+    h->kind = kind;
+    h->d = d;
+    h->device = device;
+    h->ops = ops;
+    h->params.assign(std::max<size_t>(1, ops.dn_bytes / sizeof(double)), 0.0);
+    if (nparams) memcpy(h->params.data(), params, sizeof(double) * nparams);
+    *out = h;
+    return KMC_OK;
+}
+
+int32_t kmc_density_destroy(kmc_density_t h) {
+    delete h;
+    return KMC_OK;
+}
+
+int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, double *logp_out) {
+    if (!h || !thetas || !logp_out || nw < 0) return fail(KMC_ERR_INVALID, "bad argument");
+    if (nw == 0) return KMC_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    double *dx = nullptr, *dl = nullptr;
+    CU_TRY(cudaMalloc(&dx, sizeof(double) * nw * h->d));
+    cudaError_t e = cudaMalloc(&dl, sizeof(double) * nw);
+    if (e == cudaSuccess) e = cudaMemcpy(dx, thetas, sizeof(double) * nw * h->d, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        long long nwl = nw;
+        void *args[] = {&dx, &dl, &nwl, h->params.data()};
+        e = cudaLaunchKernel(h->ops.eval, dim3((unsigned)((nw + 255) / 256)), dim3(256), args, 0, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(logp_out, dl, sizeof(double) * nw, cudaMemcpyDeviceToHost);
+    cudaFree(dx);
+    cudaFree(dl);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "density eval failed: %s", cudaGetErrorString(e));
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_destroy(kmc_sampler_t s) {
+    if (!s) return KMC_OK;
+    cudaSetDevice(s->opts.device);
+    cudaFree(s->x);
+    cudaFree(s->lp);
+    cudaFree(s->chain_x);
+    cudaFree(s->chain_lp);
+    cudaFree(s->nacc);
+    cudaFree(s->barrier);
+    cudaFree(s->rp_partner);
+    cudaFree(s->rp_z);
+    cudaFree(s->rp_u);
+    cudaFree(s->scratch);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t nwalkers, int32_t d,
+                         const kmc_emcee_opts *opts, kmc_sampler_t *out) {
+    if (!out) return fail(KMC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!density || !theta0s || !opts) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (d != density->d) return fail(KMC_ERR_INVALID, "d=%d does not match the density (d=%d)", d, density->d);
+    // the reference's asserts, src/samplers.jl:200-205
+    if (!(opts->a_scale > 1.0)) return fail(KMC_ERR_INVALID, "a_scale must be > 1");
+    if (nwalkers < 2 || (nwalkers & 1)) return fail(KMC_ERR_INVALID, "Use an even number of walkers.");
+    if (nwalkers < (int64_t)d + 2)
+        return fail(KMC_ERR_INVALID, "Use more walkers: at least DOF+2, but better many more.");
+    if (opts->nthin < 1) return fail(KMC_ERR_INVALID, "nthin must be >= 1");
+    if (opts->niter_walker < 0 || opts->nburnin_walker < 0)
+        return fail(KMC_ERR_INVALID, "niter and nburnin must be >= 0");
+    if (nwalkers / 2 >= (1LL << 32)) return fail(KMC_ERR_INVALID, "too many walkers");
+    if (opts->mode != KMC_MODE_PHILOX && opts->mode != KMC_MODE_REPLAY)
+        return fail(KMC_ERR_INVALID, "unknown mode %d", opts->mode);
+
+    CU_TRY(cudaSetDevice(opts->device));
+    auto *s = new kmc_sampler_s;
+    s->dn = density;
+    s->opts = *opts;
+    s->nw = nwalkers;
+    s->nhalf = nwalkers / 2;
+    s->d = d;
+    const long long nspan = opts->niter_walker - opts->nburnin_walker;
+    s->ns = nspan > 0 ? nspan / opts->nthin : 0;  // :234
+
+    auto bail = [&](int32_t rc) {
+        kmc_emcee_destroy(s);
+        return rc;
+    };
+#define CU_TRY_S(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return bail(fail(KMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                             __FILE__, __LINE__));                                                  \
+    } while (0)
+
+    CU_TRY_S(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    s->stream = s->own_stream;
+    CU_TRY_S(cudaEventCreate(&s->ev0));
+    CU_TRY_S(cudaEventCreate(&s->ev1));
+    CU_TRY_S(cudaMalloc(&s->x, sizeof(double) * s->nw * d));
+    CU_TRY_S(cudaMalloc(&s->lp, sizeof(double) * s->nw));
+    CU_TRY_S(cudaMalloc(&s->nacc, sizeof(unsigned) * s->nw));
+    CU_TRY_S(cudaMalloc(&s->barrier, sizeof(unsigned long long)));
+    CU_TRY_S(cudaMalloc(&s->scratch, 4 * sizeof(unsigned long long)));
+    if (s->ns > 0) {
+        CU_TRY_S(cudaMalloc(&s->chain_x, sizeof(double) * s->ns * s->nw * d));
+        CU_TRY_S(cudaMalloc(&s->chain_lp, sizeof(double) * s->ns * s->nw));
+    }
+    CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nw, s->stream));
+    CU_TRY_S(cudaMemsetAsync(s->barrier, 0, sizeof(unsigned long long), s->stream));
+    CU_TRY_S(cudaMemcpyAsync(s->x, theta0s, sizeof(double) * s->nw * d, cudaMemcpyHostToDevice, s->stream));
+    {  // initial log-densities, :209-210
+        long long nwl = s->nw;
+        void *args[] = {&s->x, &s->lp, &nwl, density->params.data()};
+        CU_TRY_S(cudaLaunchKernel(density->ops.eval, dim3((unsigned)((s->nw + 255) / 256)), dim3(256), args, 0,
+                                  s->stream));
+    }
+    int nsm = 0;
+    CU_TRY_S(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, opts->device));
+    for (int r = 0; r < 2; ++r) {
+        int per_sm = 0;
+        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, density->ops.run[r], 256, 0));
+        s->max_blocks[r] = per_sm * nsm;
+        if (s->max_blocks[r] < 1) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
+    }
+    CU_TRY_S(cudaStreamSynchronize(s->stream));
+#undef CU_TRY_S
+    *out = s;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_set_stream(kmc_sampler_t s, void *cuda_stream) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? (cudaStream_t)cuda_stream : s->own_stream;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_set_replay(kmc_sampler_t s, const int64_t *partner, const double *z, const double *u,
+                             int64_t niters) {
+    if (!s || !partner || !z || !u || niters < 0) return fail(KMC_ERR_INVALID, "bad argument");
+    if (s->opts.mode != KMC_MODE_REPLAY) return fail(KMC_ERR_STATE, "sampler is not in replay mode");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    const long long n = niters * s->nw;
+    for (long long i = 0; i < n; ++i)
+        if (partner[i] < 0 || partner[i] >= s->nw)
+            return fail(KMC_ERR_INVALID, "replay partner %lld at slot %lld is outside [0, nwalkers)",
+                        (long long)partner[i], i);
+    cudaFree(s->rp_partner);
+    cudaFree(s->rp_z);
+    cudaFree(s->rp_u);
+    s->rp_partner = nullptr;
+    s->rp_z = s->rp_u = nullptr;
+    s->rp_niters = 0;
+    if (n > 0) {
+        CU_TRY(cudaMalloc(&s->rp_partner, sizeof(long long) * n));
+        CU_TRY(cudaMalloc(&s->rp_z, sizeof(double) * n));
+        CU_TRY(cudaMalloc(&s->rp_u, sizeof(double) * n));
+        CU_TRY(cudaMemcpy(s->rp_partner, partner, sizeof(long long) * n, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(s->rp_z, z, sizeof(double) * n, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(s->rp_u, u, sizeof(double) * n, cudaMemcpyHostToDevice));
+    }
+    s->rp_t0 = s->iters_done;
+    s->rp_niters = niters;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    const long long remaining = s->opts.niter_walker - s->iters_done;
+    if (niters < 0 || niters > remaining) niters = remaining;
+    s->last_launches = 0;
+    s->timed = false;
+    if (niters <= 0) return KMC_OK;
+    const bool replay = s->opts.mode == KMC_MODE_REPLAY;
+    if (replay && (s->iters_done < s->rp_t0 || s->iters_done + niters > s->rp_t0 + s->rp_niters))
+        return fail(KMC_ERR_STATE, "replay draws cover iterations [%lld, %lld), asked to run [%lld, %lld)",
+                    s->rp_t0, s->rp_t0 + s->rp_niters, s->iters_done, s->iters_done + niters);
+    CU_TRY(cudaSetDevice(s->opts.device));
+
+    kmc::RunParams p{};
+    p.x = s->x;
+    p.lp = s->lp;
+    p.nacc = s->nacc;
+    p.chain_x = s->chain_x;
+    p.chain_lp = s->chain_lp;
+    p.rp_partner = s->rp_partner;
+    p.rp_z = s->rp_z;
+    p.rp_u = s->rp_u;
+    p.rp_t0 = s->rp_t0;
+    p.nw = s->nw;
+    p.nhalf = s->nhalf;
+    p.nthin = s->opts.nthin;
+    p.ns = s->ns;
+    const double a = s->opts.a_scale;
+    p.sia = std::sqrt(1.0 / a);
+    p.span = std::sqrt(a) - p.sia;
+    p.nm1 = (double)(s->d - 1);
+    p.seed = s->opts.seed;
+    p.id_base = s->opts.walker_id_base;
+    p.id_half_stride = s->nhalf;
+    const unsigned nh = (unsigned)s->nhalf;
+    p.lemire_t = (unsigned)(0u - nh) % nh;
+    p.barrier = s->barrier;
+
+    auto set_range = [&](long long h0, long long h1) {
+        p.h0 = h0;
+        p.h1 = h1;
+        const long long t = h0 >> 1;
+        p.n0 = t + 1 - s->opts.nburnin_walker;  // :245  n = (1-nburnin_walker) + t
+        long long ph = p.n0 % p.nthin;
+        if (ph < 0) ph += p.nthin;
+        p.phase0 = ph;
+        p.sidx0 = p.n0 >= 1 ? (p.n0 - 1) / p.nthin : 0;
+        p.bar_base = s->bar_base;
+    };
+
+    const long long hbeg = 2 * s->iters_done, hend = 2 * (s->iters_done + niters);
+    const void *kern = s->dn->ops.run[replay ? 1 : 0];
+    void *args[] = {&p, s->dn->params.data()};
+    CU_TRY(cudaEventRecord(s->ev0, s->stream));
+    if (s->opts.launch_mode == 1) {
+        const unsigned grid = (unsigned)((s->nhalf + 255) / 256);
+        for (long long h = hbeg; h < hend; ++h) {
+            set_range(h, h + 1);
+            CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
+            ++s->last_launches;
+        }
+    } else {
+        long long want = (s->nhalf + 255) / 256;
+        const unsigned grid = (unsigned)std::min<long long>(want, s->max_blocks[replay ? 1 : 0]);
+        set_range(hbeg, hend);
+        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
+        s->bar_base += (unsigned long long)(hend - hbeg - 1) * grid;
+        ++s->last_launches;
+    }
+    CU_TRY(cudaEventRecord(s->ev1, s->stream));
+    s->timed = true;
+    s->iters_done += niters;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_sync(kmc_sampler_t s) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_last_run_ms(kmc_sampler_t s, double *ms, int64_t *launches) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    if (launches) *launches = s->last_launches;
+    if (ms) *ms = 0.0;
+    if (!s->timed) return KMC_OK;
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaEventSynchronize(s->ev1));
+    float f = 0.f;
+    CU_TRY(cudaEventElapsedTime(&f, s->ev0, s->ev1));
+    if (ms) *ms = f;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_progress(kmc_sampler_t s, int64_t *iters_done, double *naccept_mean, double *naccept_std,
+                           int64_t *outliers) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    unsigned long long *sum = s->scratch, *outl = s->scratch + 1;
+    double *ssq = reinterpret_cast<double *>(s->scratch + 2);
+    CU_TRY(cudaMemsetAsync(s->scratch, 0, 4 * sizeof(unsigned long long), s->stream));
+    const unsigned grid = (unsigned)std::min<long long>((s->nw + 255) / 256, 1184);
+    kmc::nacc_sum_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, sum);
+    unsigned long long hsum = 0, houtl = 0;
+    double hssq = 0.0;
+    CU_TRY(cudaMemcpyAsync(&hsum, sum, sizeof hsum, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    const double mean = (double)hsum / (double)s->nw;  // :276
+    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, mean, -1.0, ssq, nullptr);
+    CU_TRY(cudaMemcpyAsync(&hssq, ssq, sizeof hssq, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    const double sd = std::sqrt(hssq / (double)(s->nw - 1));  // :277 sqrt(var(naccept))
+    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, mean, 2.0 * sd, nullptr, outl);  // :278
+    CU_TRY(cudaMemcpyAsync(&houtl, outl, sizeof houtl, cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    CU_TRY(cudaGetLastError());
+    if (iters_done) *iters_done = s->iters_done;
+    if (naccept_mean) *naccept_mean = mean;
+    if (naccept_std) *naccept_std = sd;
+    if (outliers) *outliers = (int64_t)houtl;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_nsamples(kmc_sampler_t s, int64_t *ns) {
+    if (!s || !ns) return fail(KMC_ERR_INVALID, "NULL argument");
+    *ns = s->ns;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, double *accept_ratio) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    const long long ns = s->ns, nw = s->nw;
+    const int d = s->d;
+    if (ns > 0 && (thetas || logp)) {
+        // walkers per staging chunk: <= 64 MiB of [wc][ns][d] doubles
+        long long wc = std::max<long long>(32, (64LL << 20) / (sizeof(double) * ns * d));
+        wc = std::min(wc, nw);
+        double *stage = nullptr;
+        CU_TRY(cudaMalloc(&stage, sizeof(double) * wc * ns * d));
+        cudaError_t e = cudaSuccess;
+        for (long long w0 = 0; w0 < nw && e == cudaSuccess; w0 += wc) {
+            const long long cur = std::min(wc, nw - w0);
+            const dim3 blk(32, 8);
+            if (thetas) {
+                const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), (unsigned)d);
+                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_x, stage, ns, nw, w0, cur, d);
+                e = cudaMemcpyAsync(thetas + w0 * ns * d, stage, sizeof(double) * cur * ns * d,
+                                    cudaMemcpyDeviceToHost, s->stream);
+                if (e != cudaSuccess) break;
+            }
+            if (logp) {
+                const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), 1);
+                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_lp, stage, ns, nw, w0, cur, 1);
+                e = cudaMemcpyAsync(logp + w0 * ns, stage, sizeof(double) * cur * ns, cudaMemcpyDeviceToHost,
+                                    s->stream);
+            }
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+        if (e == cudaSuccess) e = cudaGetLastError();
+        cudaFree(stage);
+        if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "copy_results failed: %s", cudaGetErrorString(e));
+    }
+    if (accept_ratio) {
+        std::vector<unsigned> h(nw);
+        CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * nw, cudaMemcpyDeviceToHost));
+        const double den = (double)(s->opts.niter_walker - s->opts.nburnin_walker);  // :291
+        for (long long w = 0; w < nw; ++w) accept_ratio[w] = (double)h[w] / den;
+    }
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (theta) CU_TRY(cudaMemcpy(theta, s->x, sizeof(double) * s->nw * s->d, cudaMemcpyDeviceToHost));
+    if (logp) CU_TRY(cudaMemcpy(logp, s->lp, sizeof(double) * s->nw, cudaMemcpyDeviceToHost));
+    if (naccept) {
+        std::vector<unsigned> h(s->nw);
+        CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * s->nw, cudaMemcpyDeviceToHost));
+        for (long long w = 0; w < s->nw; ++w) naccept[w] = h[w];
+    }
+    return KMC_OK;
+}
+
+}  // extern "C"
