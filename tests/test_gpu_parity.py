@@ -1,0 +1,235 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C-ABI, against the CPU oracle
+and the committed golden fixtures.  Bit-exact on decisions, partner indices, chains and
+log-densities for the scalar FP64 plugins (tolerance 0): both sides perform the same IEEE
+binary64 operations without FMA contraction.  The only non-shared arithmetic is log(): the
+fixtures record the smallest |lhs - log u| of any decision (>= 1e-9), so a 1-ulp difference
+between glibc and CUDA log cannot flip a decision."""
+import math
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from tests import cases
+from tests.test_oracle import REFERENCE_CASES, _moments_ok, edge_case_draws
+
+pytestmark = pytest.mark.gpu
+GOLDEN = Path(__file__).resolve().parent / "golden"
+ALL_CASES = ["exponential", "exponential3", "rosenbrock", "normal", "mvn2", "mvn10", "lognormal"]
+
+
+def _pair(km, orc, case):
+    name, d, params, th0, rad = cases.plugin_specs()[case]
+    return km.LogDensity(name, d, params), orc.Density(name, d, params), th0, rad
+
+
+def _start(case, th0, rad, nw, seed):
+    x = cases.ball(th0, rad, nw, seed)
+    return np.abs(x) if case.startswith(("exponential", "lognormal")) else x
+
+
+def _run_gpu(km, ld, x0, nitw, nbw, nthin, a, seed=0, replay=None, launch_mode=0, chunks=None):
+    mode = km.MODE_REPLAY if replay is not None else km.MODE_PHILOX
+    s = km.Sampler(ld, x0, nitw, nbw, nthin, a, seed, mode, launch_mode=launch_mode)
+    if replay is not None:
+        s.set_replay(*replay)
+    if chunks:
+        for c in chunks:
+            s.run(c)
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    return dict(chain_x=th, chain_lp=lp, accept_ratio=ar, x=x, lp=l, naccept=na)
+
+
+def _assert_same(a, b):
+    for k in ("chain_x", "chain_lp", "accept_ratio", "x", "lp", "naccept"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_device_present(km):
+    assert km.device_count() >= 1
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_density_eval_matches_oracle(km, orc, case):
+    ld, od, th0, rad = _pair(km, orc, case)
+    rng = np.random.default_rng(0)
+    pts = np.atleast_1d(np.asarray(th0, dtype=float))[None, :] + 3.0 * rng.standard_normal((1000, ld.d))
+    pts[0] = 0.0
+    pts[1] = -1.0
+    pts[2] = np.nan
+    pts[3] = 1e300
+    got, want = ld.eval(pts), od.eval(pts)
+    if case == "lognormal":     # log() is the one routine not shared bit-for-bit (CUDA vs glibc, <= 1 ulp each)
+        fin = np.isfinite(want)
+        assert np.array_equal(np.isfinite(got), fin) and np.array_equal(got[~fin], want[~fin], equal_nan=True)
+        np.testing.assert_allclose(got[fin], want[fin], rtol=1e-14, atol=1e-15)
+    else:
+        assert np.array_equal(got, want, equal_nan=True)
+    assert ld(pts[5]) == want[5] if ld.d > 1 else ld(float(pts[5, 0])) == want[5]
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_golden_replay(km, case):
+    """Replay mode against the committed fixture (no oracle involved): uploaded partner/z/u
+    must give bit-identical chains, log-densities, accept counts and final state."""
+    g = np.load(GOLDEN / f"{case}.npz")
+    ld = km.LogDensity(str(g["name"]), int(g["d"]), g["params"])
+    r = _run_gpu(km, ld, g["theta0s"], int(g["niter_walker"]), int(g["nburnin_walker"]), int(g["nthin"]),
+                 float(g["a_scale"]), replay=(g["partner"], g["z"], g["u"]))
+    tol = dict(rtol=1e-14, atol=0) if case == "lognormal" else None
+    for k, gk in (("chain_x", "chain_x"), ("chain_lp", "chain_lp"), ("accept_ratio", "accept_ratio"),
+                  ("x", "final_x"), ("lp", "final_lp"), ("naccept", "naccept")):
+        if tol and k in ("chain_lp", "lp"):
+            np.testing.assert_allclose(r[k], g[gk], **tol)
+        else:
+            assert np.array_equal(r[k], g[gk]), k
+
+
+@pytest.mark.parametrize("case", ALL_CASES)
+def test_golden_philox(km, case):
+    """Free-running mode: the device Philox stream, partner mapping and z transform reproduce the
+    fixture's recorded draws, so the whole run is bit-identical."""
+    g = np.load(GOLDEN / f"{case}.npz")
+    ld = km.LogDensity(str(g["name"]), int(g["d"]), g["params"])
+    r = _run_gpu(km, ld, g["theta0s"], int(g["niter_walker"]), int(g["nburnin_walker"]), int(g["nthin"]),
+                 float(g["a_scale"]), seed=int(g["seed"]))
+    assert np.array_equal(r["chain_x"], g["chain_x"]) and np.array_equal(r["naccept"], g["naccept"])
+    assert np.array_equal(r["x"], g["final_x"])
+    if case == "lognormal":
+        np.testing.assert_allclose(r["chain_lp"], g["chain_lp"], rtol=1e-14)
+    else:
+        assert np.array_equal(r["chain_lp"], g["chain_lp"])
+
+
+@pytest.mark.parametrize("case,nw,nitw,nbw,nthin,a", [
+    ("exponential", 100, 1000, 500, 1, 2.0),        # README config (BASELINE.json configs[0])
+    ("rosenbrock", 4096, 200, 100, 7, 2.0),
+    ("rosenbrock", 4, 50, 0, 1, 2.0),               # minimum ensemble: nw = d + 2
+    ("mvn2", 1000, 120, 40, 3, 3.5),
+    ("mvn10", 512, 60, 20, 2, 2.0),
+    ("exponential3", 300, 80, 80, 1, 2.0),          # burn-in == niter -> no samples
+    ("normal", 50, 0, 0, 1, 2.0),                   # niter < nwalkers -> niter_walker = 0
+])
+def test_seeded_oracle_parity(km, orc, case, nw, nitw, nbw, nthin, a):
+    """Same seed, same inputs: oracle (Philox) vs CUDA (Philox) vs CUDA (replay of the oracle's trace)."""
+    ld, od, th0, rad = _pair(km, orc, case)
+    x0 = _start(case, th0, rad, nw, 21)
+    want = orc.emcee(od, x0, nitw, nbw, nthin, a, seed=99, trace=True, nthreads=4)
+    if want["trace"][0].size:
+        assert want["min_margin"] > 1e-11
+    got = _run_gpu(km, ld, x0, nitw, nbw, nthin, a, seed=99)
+    _assert_same(got, want)
+    if nitw:
+        rep = _run_gpu(km, ld, x0, nitw, nbw, nthin, a, replay=want["trace"][:3])
+        _assert_same(rep, want)
+    assert got["chain_x"].shape == (nw, (nitw - nbw) // nthin, ld.d)
+
+
+def test_launch_modes_and_chunking_agree(km):
+    """Persistent kernel (grid barrier) == one launch per half-step == arbitrary run() chunking."""
+    ld = km.rosenbrock()
+    x0 = cases.ball([0, 0], 0.1, 20000, 3)
+    a = _run_gpu(km, ld, x0, 60, 25, 4, 2.0, seed=5, launch_mode=0)
+    b = _run_gpu(km, ld, x0, 60, 25, 4, 2.0, seed=5, launch_mode=1)
+    c = _run_gpu(km, ld, x0, 60, 25, 4, 2.0, seed=5, launch_mode=0, chunks=[1, 7, 24, 1, 13])
+    _assert_same(a, b)
+    _assert_same(a, c)
+
+
+def test_accept_edge_cases_on_device(km, orc):
+    """src/samplers.jl:260 `>=`, -Inf proposals, u == 0, NaN -- same decisions as the oracle."""
+    x0 = np.array([[1.0], [6.0], [3.0], [4.0]])
+    r = _run_gpu(km, km.exponential(), x0, 1, 0, 1, 2.0, replay=edge_case_draws())
+    assert r["x"][:, 0].tolist() == [1.0, 6.0, -1.5, 4.0]
+    assert r["lp"].tolist() == [-1.0, -6.0, -np.inf, -4.0]
+    assert r["naccept"].tolist() == [0, 1, 1, 0]
+
+
+def test_replay_validation(km):
+    ld = km.rosenbrock()
+    x0 = cases.ball([0, 0], 0.1, 8, 0)
+    s = km.Sampler(ld, x0, 4, 0, 1, 2.0, 0, km.MODE_REPLAY)
+    with pytest.raises(km.KmcError):
+        s.run(1)                                   # no draws uploaded
+    bad = np.full(8, 99, dtype=np.int64)
+    with pytest.raises(km.KmcError):
+        s.set_replay(bad, np.ones(8), np.ones(8))  # partner outside the ensemble
+    s.close()
+    with pytest.raises(km.KmcError, match="even number"):
+        km.Sampler(ld, x0[:7], 4, 0)
+    with pytest.raises(km.KmcError, match="a_scale"):
+        km.Sampler(ld, x0, 4, 0, a_scale=0.5)
+    with pytest.raises(km.KmcError, match="DOF"):
+        km.Sampler(ld, x0[:2], 4, 0)
+
+
+@pytest.mark.parametrize("case,niter,tol,mean,std,median,skew", REFERENCE_CASES)
+def test_reference_testcases_through_public_api(km, case, niter, tol, mean, std, median, skew):
+    """The reference's own emcee testset (test/emcee.jl:17-48) through make_theta0s -> emcee ->
+    squash_walkers: shapes, 4th output None, accept_ratio > 0.1, moments within tol*std."""
+    name, d, params, th0, rad = cases.plugin_specs()[case]
+    ld = km.LogDensity(name, d, params)
+    nw = 100
+    theta0s = km.make_theta0s(th0, rad, ld, nw, seed=4)
+    samples = km.emcee(ld, theta0s, niter=niter, use_progress_meter=False, seed=8)
+    assert tuple(len(v) for v in samples[:3]) == (nw, nw, nw)
+    assert samples[3] is None
+    assert len(samples[0][0]) == niter // nw // 2
+    thetas, ar, logd, blobs = km.squash_walkers(*samples, verbose=False)
+    assert blobs is None and len(thetas) == niter // 2 and len(logd) == niter // 2
+    assert ar > 0.1
+    _moments_ok(thetas, mean, std, tol, median, skew)
+
+
+def test_readme_example(km, capsys):
+    """README.md:12-34 (BASELINE.json configs[0]) with the default progress meter on."""
+    ld = km.exponential()
+    thetas, ar, _, _ = km.emcee(ld, km.make_theta0s(0.5, 0.1, ld, 100), niter=10**5)
+    t, a, _, _ = km.squash_walkers(thetas, ar)
+    assert thetas.shape == (100, 500) and t.shape == (50000,)
+    assert np.all(t >= 0) and abs(t.mean() - 1) < 0.1 and abs(t.std() - 1) < 0.1
+    assert abs(a - 0.746) < 0.03
+    assert "accept_ratio_mean" in capsys.readouterr().err
+
+
+def test_progress_statistics(km):
+    """kmc_emcee_progress == mean / sqrt(var) / outlier count of naccept (src/samplers.jl:276-278)."""
+    ld = km.rosenbrock()
+    s = km.Sampler(ld, cases.ball([0, 0], 0.1, 5000, 1), 80, 0, 1, 2.0, 3)
+    s.run(50)
+    it, mean, sd, outl = s.progress()
+    _, _, na = s.state()
+    assert it == 50 and mean == pytest.approx(na.mean(), rel=1e-12)
+    assert sd == pytest.approx(na.std(ddof=1), rel=1e-9)
+    assert outl == int(np.sum(np.abs(na - na.mean()) > 2 * na.std(ddof=1)))
+    s.close()
+
+
+def test_full_size_properties_config2(km):
+    """BASELINE.json configs[1] at full width (2^20 walkers, Rosenbrock) for 64 iterations, checked
+    through size-independent properties: (1) every stored log-density equals the plugin evaluated
+    at the stored theta; (2) per-walker accept counts equal the number of state changes in the
+    unthinned chain; (3) persistent and per-half-step launch modes give identical checksums."""
+    ld = km.rosenbrock()
+    nw = 1 << 20
+    x0 = cases.ball([0, 0], 0.1, nw, 77)
+    s = km.Sampler(ld, x0, 64, 32, 1, 2.0, 1234)
+    s.run(-1)
+    th, lp, ar = s.results()
+    xf, lf, na = s.state()
+    s.close()
+    assert th.shape == (nw, 32, 2)
+    sub = slice(0, nw, 37)
+    assert np.array_equal(ld.eval(th[sub].reshape(-1, 2)), lp[sub].reshape(-1))
+    assert np.array_equal(th[:, -1], xf) and np.array_equal(lp[:, -1], lf)
+    changes = np.sum(np.any(th[:, 1:] != th[:, :-1], axis=2), axis=1)
+    assert np.all(changes <= na) and np.all(na - changes <= 1)      # the first post-burn-in move has no predecessor stored
+    assert 0.2 < ar.mean() < 0.8
+    s2 = km.Sampler(ld, x0, 64, 32, 1, 2.0, 1234, launch_mode=1)
+    s2.run(-1)
+    x2, l2, na2 = s2.state()
+    s2.close()
+    assert np.array_equal(xf, x2) and np.array_equal(lf, l2) and np.array_equal(na, na2)
