@@ -38,7 +38,9 @@ int32_t fail(int32_t code, const char *fmt, ...) {
 
 // ------------------------------------------------------------------ kernel registry
 struct Ops {
-    const void *run[2] = {nullptr, nullptr};  // [replay]
+    const void *run[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [replay][smem-resident state]
+    size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
+    int block = 0;               // threads per CTA of the run kernels
     const void *eval = nullptr;
     size_t dn_bytes = 0;
     int nparams = 0;
@@ -47,8 +49,12 @@ struct Ops {
 template <template <int> class Dn, int D>
 Ops make_ops() {
     Ops o;
-    o.run[0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
-    o.run[1] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
+    o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false, false>;
+    o.run[0][1] = (const void *)kmc::emcee_run_kernel<Dn, D, false, true>;
+    o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true, false>;
+    o.run[1][1] = (const void *)kmc::emcee_run_kernel<Dn, D, true, true>;
+    o.smem_per_walker = 8 * D + 8 + 4;
+    o.block = kmc::block_threads<D>();
     o.eval = (const void *)kmc::density_eval_kernel<Dn, D>;
     o.dn_bytes = sizeof(Dn<D>);
     o.nparams = Dn<D>::nparams;
@@ -125,7 +131,9 @@ struct kmc_sampler_s {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     long long last_launches = 0;
-    int max_blocks[2] = {0, 0};  // co-resident CTAs of run[replay]
+    int nsm = 0;
+    unsigned grid = 1, per_cta = 1;  // persistent launch geometry
+    size_t smem_bytes = 0;           // > 0: owned state is shared-memory resident
     unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
 };
 
@@ -282,13 +290,28 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         CU_TRY_S(cudaLaunchKernel(density->ops.eval, dim3((unsigned)((s->nw + 255) / 256)), dim3(256), args, 0,
                                   s->stream));
     }
-    int nsm = 0;
-    CU_TRY_S(cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, opts->device));
-    for (int r = 0; r < 2; ++r) {
+    CU_TRY_S(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, opts->device));
+    {   // persistent launch geometry: every CTA owns per_cta walker positions of each half
+        const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
+        const int blk = density->ops.block;
         int per_sm = 0;
-        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, density->ops.run[r], 256, 0));
-        s->max_blocks[r] = per_sm * nsm;
-        if (s->max_blocks[r] < 1) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
+        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, density->ops.run[r][0], blk, 0));
+        if (per_sm < 1) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
+        const long long want = (s->nhalf + blk - 1) / blk;
+        s->grid = (unsigned)std::min<long long>(want, (long long)per_sm * s->nsm);
+        s->per_cta = (unsigned)((s->nhalf + s->grid - 1) / s->grid);
+        s->grid = (unsigned)((s->nhalf + s->per_cta - 1) / s->per_cta);
+        // shared-memory residency of the owned state if all CTAs still fit on the device
+        const size_t need = (size_t)2 * s->per_cta * density->ops.smem_per_walker;
+        int max_optin = 0;
+        CU_TRY_S(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opts->device));
+        if (opts->launch_mode == 0 && need <= (size_t)max_optin) {
+            const void *k = density->ops.run[r][1];
+            CU_TRY_S(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
+            int per_sm_s = 0;
+            CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k, blk, need));
+            if ((long long)per_sm_s * s->nsm >= (long long)s->grid) s->smem_bytes = need;
+        }
     }
     CU_TRY_S(cudaStreamSynchronize(s->stream));
 #undef CU_TRY_S
@@ -358,13 +381,15 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     p.rp_u = s->rp_u;
     p.rp_t0 = s->rp_t0;
     p.nw = s->nw;
-    p.nhalf = s->nhalf;
+    p.nhalf = (unsigned)s->nhalf;
     p.nthin = s->opts.nthin;
     p.ns = s->ns;
     const double a = s->opts.a_scale;
     p.sia = std::sqrt(1.0 / a);
     p.span = std::sqrt(a) - p.sia;
     p.nm1 = (double)(s->d - 1);
+    p.nm1f = (float)(s->d - 1);
+    p.margin = (float)((p.nm1 + 64.0) * 2e-6);
     p.seed = s->opts.seed;
     p.id_base = s->opts.walker_id_base;
     p.id_half_stride = s->nhalf;
@@ -385,22 +410,24 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     };
 
     const long long hbeg = 2 * s->iters_done, hend = 2 * (s->iters_done + niters);
-    const void *kern = s->dn->ops.run[replay ? 1 : 0];
     void *args[] = {&p, s->dn->params.data()};
+    p.per_cta = s->per_cta;
+    const int blk = s->dn->ops.block;
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
     if (s->opts.launch_mode == 1) {
-        const unsigned grid = (unsigned)((s->nhalf + 255) / 256);
+        const void *kern = s->dn->ops.run[replay ? 1 : 0][0];
+        p.per_cta = blk;
+        const unsigned grid = (unsigned)((s->nhalf + blk - 1) / blk);
         for (long long h = hbeg; h < hend; ++h) {
             set_range(h, h + 1);
-            CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
+            CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(blk), args, 0, s->stream));
             ++s->last_launches;
         }
     } else {
-        long long want = (s->nhalf + 255) / 256;
-        const unsigned grid = (unsigned)std::min<long long>(want, s->max_blocks[replay ? 1 : 0]);
+        const void *kern = s->dn->ops.run[replay ? 1 : 0][s->smem_bytes ? 1 : 0];
         set_range(hbeg, hend);
-        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(256), args, 0, s->stream));
-        s->bar_base += (unsigned long long)(hend - hbeg - 1) * grid;
+        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(blk), args, s->smem_bytes, s->stream));
+        s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid;
         ++s->last_launches;
     }
     CU_TRY(cudaEventRecord(s->ev1, s->stream));
