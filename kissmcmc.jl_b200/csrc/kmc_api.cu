@@ -40,7 +40,8 @@ int32_t fail(int32_t code, const char *fmt, ...) {
 struct Ops {
     const void *run[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [replay][smem-resident state]
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
-    int block = 0;               // threads per CTA of the run kernels
+    int block = 0;               // max threads per CTA of the run kernels
+    int min_blocks = 1;          // CTAs per SM the kernels are compiled for
     const void *eval = nullptr;
     size_t dn_bytes = 0;
     int nparams = 0;
@@ -49,12 +50,15 @@ struct Ops {
 template <template <int> class Dn, int D>
 Ops make_ops() {
     Ops o;
-    o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false, false>;
-    o.run[0][1] = (const void *)kmc::emcee_run_kernel<Dn, D, false, true>;
-    o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true, false>;
-    o.run[1][1] = (const void *)kmc::emcee_run_kernel<Dn, D, true, true>;
+    o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
+    o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
+    if (D <= 4) {  // shared-memory-resident variant for small rows
+        o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;
+        o.run[1][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), true>;
+    }
     o.smem_per_walker = 8 * D + 8 + 4;
-    o.block = kmc::block_threads<D>();
+    o.block = kmc::max_threads<D>();
+    o.min_blocks = kmc::min_blocks<D>();
     o.eval = (const void *)kmc::density_eval_kernel<Dn, D>;
     o.dn_bytes = sizeof(Dn<D>);
     o.nparams = Dn<D>::nparams;
@@ -132,8 +136,9 @@ struct kmc_sampler_s {
     bool timed = false;
     long long last_launches = 0;
     int nsm = 0;
-    unsigned grid = 1, per_cta = 1;  // persistent launch geometry
-    size_t smem_bytes = 0;           // > 0: owned state is shared-memory resident
+    unsigned grid = 1, per_cta = 1, block = 32;  // persistent launch geometry
+    size_t smem_bytes = 0;
+    bool use_smem = false;           // owned state is shared-memory resident (emcee_smem_kernel)
     unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
 };
 
@@ -179,6 +184,10 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
     h->ops = ops;
     h->params.assign(std::max<size_t>(1, ops.dn_bytes / sizeof(double)), 0.0);
     if (nparams) memcpy(h->params.data(), params, sizeof(double) * nparams);
+    if (kind == kmc::KIND_ROSENBROCK) {  // RN(1/T) for the exact reciprocal-based division (ddiv_by)
+        const double T = std::fabs(params[2]);
+        h->params[3] = (T > 0x1p-100 && T < 0x1p100) ? 1.0 / params[2] : 0.0;
+    }
     *out = h;
     return KMC_OK;
 }
@@ -291,26 +300,40 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
                                   s->stream));
     }
     CU_TRY_S(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, opts->device));
-    {   // persistent launch geometry: every CTA owns per_cta walker positions of each half
+    {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
+        // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
-        const int blk = density->ops.block;
-        int per_sm = 0;
-        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, density->ops.run[r][0], blk, 0));
-        if (per_sm < 1) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
-        const long long want = (s->nhalf + blk - 1) / blk;
-        s->grid = (unsigned)std::min<long long>(want, (long long)per_sm * s->nsm);
-        s->per_cta = (unsigned)((s->nhalf + s->grid - 1) / s->grid);
-        s->grid = (unsigned)((s->nhalf + s->per_cta - 1) / s->per_cta);
-        // shared-memory residency of the owned state if all CTAs still fit on the device
-        const size_t need = (size_t)2 * s->per_cta * density->ops.smem_per_walker;
-        int max_optin = 0;
-        CU_TRY_S(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opts->device));
-        if (opts->launch_mode == 0 && need <= (size_t)max_optin) {
-            const void *k = density->ops.run[r][1];
-            CU_TRY_S(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need));
-            int per_sm_s = 0;
-            CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_s, k, blk, need));
-            if ((long long)per_sm_s * s->nsm >= (long long)s->grid) s->smem_bytes = need;
+        auto geometry = [&](const void *kern, int maxblk, int ctas_per_sm, size_t smem_per_walker, bool &fits) {
+            const long long want = (s->nhalf + maxblk - 1) / maxblk;
+            s->grid = (unsigned)std::min<long long>(want, (long long)ctas_per_sm * s->nsm);
+            s->per_cta = (unsigned)((s->nhalf + s->grid - 1) / s->grid);
+            s->grid = (unsigned)((s->nhalf + s->per_cta - 1) / s->per_cta);
+            const unsigned rounds = (s->per_cta + maxblk - 1) / maxblk;
+            s->block = std::min<unsigned>(maxblk, (((s->per_cta + rounds - 1) / rounds + 31) / 32) * 32);
+            s->smem_bytes = (size_t)2 * s->per_cta * smem_per_walker;
+            if (s->smem_bytes > 48 * 1024) {
+                cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s->smem_bytes);
+                if (e != cudaSuccess) { cudaGetLastError(); fits = false; return rounds; }
+            }
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, (int)s->block, s->smem_bytes) != cudaSuccess) {
+                cudaGetLastError();
+                per_sm = 0;
+            }
+            fits = (long long)per_sm * s->nsm >= (long long)s->grid;
+            return rounds;
+        };
+        bool fits = false;
+        s->use_smem = false;
+        if (opts->launch_mode == 0 && density->ops.run[r][1]) {  // shared-memory-resident state if it fits
+            int max_optin = 0;
+            CU_TRY_S(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opts->device));
+            const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, 2, density->ops.smem_per_walker, fits);
+            s->use_smem = fits && rounds <= (unsigned)kmc::kRounds && s->smem_bytes <= (size_t)max_optin;
+        }
+        if (!s->use_smem) {
+            geometry(density->ops.run[r][0], density->ops.block, density->ops.min_blocks, 0, fits);
+            if (!fits) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
         }
     }
     CU_TRY_S(cudaStreamSynchronize(s->stream));
@@ -390,9 +413,9 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     p.nm1 = (double)(s->d - 1);
     p.nm1f = (float)(s->d - 1);
     p.margin = (float)((p.nm1 + 64.0) * 2e-6);
-    p.seed = s->opts.seed;
-    p.id_base = s->opts.walker_id_base;
-    p.id_half_stride = s->nhalf;
+    p.keys = kmc::philox_keys(s->opts.seed);
+    p.id_base[0] = (unsigned)s->opts.walker_id_base;
+    p.id_base[1] = (unsigned)(s->opts.walker_id_base + s->nhalf);
     const unsigned nh = (unsigned)s->nhalf;
     p.lemire_t = (unsigned)(0u - nh) % nh;
     p.barrier = s->barrier;
@@ -412,11 +435,11 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     const long long hbeg = 2 * s->iters_done, hend = 2 * (s->iters_done + niters);
     void *args[] = {&p, s->dn->params.data()};
     p.per_cta = s->per_cta;
-    const int blk = s->dn->ops.block;
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
     if (s->opts.launch_mode == 1) {
         const void *kern = s->dn->ops.run[replay ? 1 : 0][0];
-        p.per_cta = blk;
+        const int blk = s->dn->ops.block >= 256 ? 256 : s->dn->ops.block;
+        p.per_cta = (unsigned)blk;  // one walker per thread, one half-step per launch
         const unsigned grid = (unsigned)((s->nhalf + blk - 1) / blk);
         for (long long h = hbeg; h < hend; ++h) {
             set_range(h, h + 1);
@@ -424,9 +447,9 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
             ++s->last_launches;
         }
     } else {
-        const void *kern = s->dn->ops.run[replay ? 1 : 0][s->smem_bytes ? 1 : 0];
+        const void *kern = s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
         set_range(hbeg, hend);
-        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(blk), args, s->smem_bytes, s->stream));
+        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(s->block), args, s->smem_bytes, s->stream));
         s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid;
         ++s->last_launches;
     }

@@ -20,40 +20,67 @@ struct Philox4 {
     uint32_t r0, r1, r2, r3;
 };
 
+// Round keys k + r*W for r = 0..9, precomputed on the host and passed in the kernel arguments
+// (constant bank), so a round is exactly 2 IMAD.WIDE + 2 three-input LOP3.
+struct PhiloxKeys {
+    uint32_t k0[10], k1[10];
+};
+
+__host__ __device__ inline PhiloxKeys philox_keys(uint64_t seed) {
+    PhiloxKeys ks;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) {
+        ks.k0[r] = a;
+        ks.k1[r] = b;
+        a += 0x9E3779B9u;
+        b += 0xBB67AE85u;
+    }
+    return ks;
+}
+
+__device__ __forceinline__ void mul_wide(uint32_t a, uint32_t b, uint32_t &hi, uint32_t &lo) {
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%1, %0}, t;\n\t}" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+}
+
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1) {
+                                                 const PhiloxKeys &ks) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        c0 = hi1 ^ c1 ^ k0;
+        uint32_t hi0, lo0, hi1, lo1;
+        mul_wide(0xD2511F53u, c0, hi0, lo0);
+        mul_wide(0xCD9E8D57u, c2, hi1, lo1);
+        c0 = hi1 ^ c1 ^ ks.k0[r];
         c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
+        c2 = hi0 ^ c3 ^ ks.k1[r];
         c3 = lo0;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
     }
     return Philox4{c0, c1, c2, c3};
+}
+
+__device__ __forceinline__ uint32_t lemire_retry(const PhiloxKeys &ks, uint32_t walker, uint32_t iter_lo,
+                                              uint32_t iter_hi, uint32_t batch, uint32_t nhalf, uint32_t lemire_t) {
+    uint32_t hi, lo, attempt = 0;
+    do {
+        ++attempt;
+        const Philox4 rr = philox4x32_10(walker, iter_lo, iter_hi, batch | (attempt << 8), ks);
+        mul_wide(rr.r0, nhalf, hi, lo);
+    } while (lo < lemire_t);
+    return hi;
 }
 
 // One walker-step's draws, in the reference's order: partner (src/samplers.jl:250), the
 // uniform behind z (:252 -> :230), the accept uniform (:260).  counter = (walker id,
 // iteration lo, iteration hi, batch | attempt<<8), key = seed.  The partner uses Lemire's
 // multiply-shift with rejection, so it is exactly uniform on [0, nhalf) like rand(range).
-__device__ __forceinline__ void draw(uint64_t seed, uint64_t walker, uint64_t iter, uint32_t batch,
-                                     uint32_t nhalf, uint32_t lemire_t, uint32_t &partner_local,
+__device__ __forceinline__ void draw(const PhiloxKeys &ks, uint32_t walker, uint32_t iter_lo, uint32_t iter_hi,
+                                     uint32_t batch, uint32_t nhalf, uint32_t lemire_t, uint32_t &partner_local,
                                      double &uz, double &uacc) {
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    const uint32_t c0 = (uint32_t)walker, c1 = (uint32_t)iter, c2 = (uint32_t)(iter >> 32);
-    const Philox4 r = philox4x32_10(c0, c1, c2, batch, k0, k1);
-    uint64_t m = (uint64_t)r.r0 * nhalf;
-    uint32_t attempt = 0;
-    while ((uint32_t)m < lemire_t) {  // probability nhalf / 2^32 per draw
-        ++attempt;
-        const Philox4 rr = philox4x32_10(c0, c1, c2, batch | (attempt << 8), k0, k1);
-        m = (uint64_t)rr.r0 * nhalf;
-    }
-    partner_local = (uint32_t)(m >> 32);
+    const Philox4 r = philox4x32_10(walker, iter_lo, iter_hi, batch, ks);
+    uint32_t hi, lo;
+    mul_wide(r.r0, nhalf, hi, lo);
+    if (lo < lemire_t)  // probability < nhalf / 2^32 per draw: kept out of line
+        hi = lemire_retry(ks, walker, iter_lo, iter_hi, batch, nhalf, lemire_t);
+    partner_local = hi;
     const uint64_t bz = ((uint64_t)r.r1 << 16) | (r.r2 >> 16);
     const uint64_t ba = ((uint64_t)(r.r2 & 0xFFFFu) << 32) | r.r3;
     uz = (double)bz * 0x1p-48;    // exact: 48-bit integer times a power of two
@@ -89,19 +116,38 @@ struct Exponential {
     }
 };
 
-// test/runtests.jl:68  -(100*(x2 - x1^2)^2 + (1 - x1)^2)/20, params [a, b, T]
+// Correctly rounded a/b from the correctly rounded reciprocal y = RN(1/b) (computed on the
+// host): two Markstein corrections, q <- q + (a - b*q)*y with exact FMA residuals.  After the
+// first correction q is a faithful quotient, so the second returns RN(a/b) (Markstein 1990;
+// Muller et al., Handbook of Floating-Point Arithmetic, thm 5.4) -- the same bits as
+// __ddiv_rn / the oracle's `/`, in 5 FP64 instructions instead of ~20.  Valid away from
+// overflow/underflow; anything else (and y == 0, set by the host when b is out of range)
+// takes __ddiv_rn.
+__device__ __forceinline__ double ddiv_by(double a, double b, double y) {
+    const double aa = fabs(a);
+    if (y != 0.0 && aa > 0x1p-900 && aa < 0x1p900) {
+        const double q0 = a * y;
+        const double r0 = fma(-b, q0, a);
+        const double q1 = fma(r0, y, q0);
+        const double r1 = fma(-b, q1, a);
+        return fma(r1, y, q1);
+    }
+    return __ddiv_rn(a, b);
+}
+
+// test/runtests.jl:68  -(100*(x2 - x1^2)^2 + (1 - x1)^2)/20, params [a, b, T] (+ RN(1/T), host-filled)
 template <int D>
 struct Rosenbrock {
     static_assert(D == 2, "rosenbrock is 2-D");
     static constexpr int kind = KIND_ROSENBROCK;
     static constexpr int nparams = 3;
-    double p[3];
+    double p[4];
     __device__ __forceinline__ double logpdf(const double (&x)[D]) const {
         const double t = dsub(x[1], dmul(x[0], x[0]));
         const double q = dmul(p[1], dmul(t, t));
         const double m = dsub(p[0], x[0]);
         const double r = dadd(q, dmul(m, m));
-        return ddiv(-r, p[2]);
+        return ddiv_by(-r, p[2], p[3]);
     }
 };
 

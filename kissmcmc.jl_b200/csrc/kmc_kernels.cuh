@@ -22,10 +22,15 @@
 
 namespace kmc {
 
-// threads per CTA of emcee_run_kernel: small rows run 2 x 512 threads per SM in <= 64 registers;
-// wider rows (more live FP64 values per walker) get up to 255 registers at 256 threads
+// Launch shape of emcee_run_kernel.  Small rows: 2 CTAs x <=448 threads per SM in <= 72
+// registers, 4 walkers in flight per thread; wider rows (more live FP64 values per walker):
+// 1 CTA x <=256 threads with up to 255 registers, 1-2 walkers in flight.
 template <int D>
-__host__ __device__ constexpr int block_threads() { return D <= 4 ? 512 : 256; }
+__host__ __device__ constexpr int max_threads() { return D <= 4 ? 448 : 256; }
+template <int D>
+__host__ __device__ constexpr int min_blocks() { return D <= 4 ? 2 : 1; }
+template <int D>
+__host__ __device__ constexpr int in_flight() { return D <= 2 ? 2 : (D <= 8 ? 2 : 1); }
 
 struct RunParams {
     double *x;          // [nw][D] row-major walker positions (theta0s, :198)
@@ -47,9 +52,8 @@ struct RunParams {
     long long nthin, ns;
     double sia, span, nm1;  // sqrt(1/a), sqrt(a)-sqrt(1/a), (N-1)
     float nm1f, margin;     // fast accept filter: (N-1) and its rigorous error margin
-    unsigned long long seed;
-    long long id_base;      // Philox walker id = id_base + batch*id_half_stride + i
-    long long id_half_stride;
+    PhiloxKeys keys;        // Philox round keys of the seed
+    unsigned id_base[2];    // Philox walker id = id_base[batch] + i (low 32 bits of the global walker index)
     unsigned lemire_t;      // (2^32 - nhalf) mod nhalf
     unsigned long long *barrier;  // grid barrier arrival counter (monotonic)
     unsigned long long bar_base;  // its value when this launch starts
@@ -60,6 +64,8 @@ struct RunParams {
 // arrive: all threads' stores -> bar.sync -> thread 0: red.release.gpu (+1)
 // wait:   thread 0 polls (relaxed), then fence.acq_rel.gpu once -> bar.sync -> everyone
 //         gathers partner rows with ld.global.cg (L2), never from L1.
+// The two halves are split so that work that does not depend on other CTAs (the next
+// half-step's Philox draws) runs between arrive and wait.
 __device__ __forceinline__ void barrier_arrive(unsigned long long *ctr) {
     asm volatile("red.release.gpu.global.add.u64 [%0], 1;" ::"l"(ctr) : "memory");
 }
@@ -73,12 +79,13 @@ __device__ __forceinline__ void barrier_wait(const unsigned long long *ctr, unsi
 
 // ------------------------------------------------------------------ accept test
 // Decides  ((N-1)*log(z) + p1) - p0 >= log(u)   (src/samplers.jl:260).
-// Fast filter: t = (p1-p0) + ln2*((N-1)*lg2f(z) - lg2f(u)) with FP32 MUFU logs; its error is
-// bounded by `margin` (set by the host: (N-1+64)*2e-6, >3x the worst case of two MUFU.LG2
-// errors (2^-22.6 absolute on the mantissa part + one FP32 rounding of the result), two
-// FP64->FP32 input roundings and one FP32 fma, for |lg2 z| <= 4 and |lg2 u| <= 100), so
-// |t| > margin decides exactly like the FP64 expression.  Anything closer, non-finite or out of the safe
-// range takes the exact FP64 path below -- the decisions are those of the exact expression.
+// Fast filter: t = (p1-p0) + ln2*q,  q = (N-1)*lg2f(z) - lg2f(u)  with FP32 MUFU logs.  The
+// error of t is bounded by `margin` (set by the host: (N-1+64)*2e-6, >3x the worst case of
+// two MUFU.LG2 errors (2^-22.6 absolute on the mantissa part + one FP32 rounding of the
+// result), two FP64->FP32 input roundings and one FP32 fma, for |lg2 z| <= 4 and
+// |lg2 u| <= 100), so |t| > margin decides exactly like the FP64 expression.  Anything closer,
+// non-finite or outside that range (q = NaN) takes the exact FP64 path: the decisions are
+// those of the exact expression, bit for bit.
 template <bool SKIP_LOGZ>
 __device__ __forceinline__ bool accept_exact(double nm1, double z, double p1, double p0, double u) {
     double lhs;
@@ -87,136 +94,146 @@ __device__ __forceinline__ bool accept_exact(double nm1, double z, double p1, do
     return lhs >= log(u);
 }
 
-template <bool SKIP_LOGZ>
-__device__ __forceinline__ bool accept_test(const RunParams &p, double z, double p1, double p0, double u) {
+__device__ __forceinline__ float lg2_approx(float v) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
+template <bool REPLAY>
+__device__ __forceinline__ float filter_q(const RunParams &p, double z, double u) {
     const float zf = (float)z, uf = (float)u;
-    if (zf > 0.0625f && zf < 16.0f && uf > 1e-30f && uf < 1e30f) {
-        const float q = fmaf(p.nm1f, __log2f(zf), -__log2f(uf));
-        const double t = (p1 - p0) + (double)q * 0.6931471805599453;
-        if (t > (double)p.margin) return true;
-        if (t < -(double)p.margin) return false;
-    }
-    return accept_exact<SKIP_LOGZ>(p.nm1, z, p1, p0, u);
+    bool ok = uf > 1e-30f;  // false for NaN
+    if constexpr (REPLAY) ok = ok && uf < 1e30f;                  // Philox: u < 1 always
+    ok = ok && zf > 0.0625f && zf < 16.0f;
+    const float q = fmaf(p.nm1f, lg2_approx(zf), -lg2_approx(uf));
+    return ok ? q : CUDART_NAN_F;
 }
 
 // ------------------------------------------------------------------ draws for one walker-step
 template <bool REPLAY>
-__device__ __forceinline__ void step_draws(const RunParams &p, long long t, int batch, unsigned i, unsigned &j,
-                                           double &z, double &u) {
+__device__ __forceinline__ void step_draws(const RunParams &p, long long h, unsigned i, unsigned &j, double &z,
+                                           double &u) {
     if constexpr (REPLAY) {
-        const long long slot = ((t - p.rp_t0) * 2 + batch) * (long long)p.nhalf + i;
+        const long long slot = (h - 2 * p.rp_t0) * (long long)p.nhalf + i;
         j = (unsigned)__ldcs(p.rp_partner + slot);  // global 0-based index
         z = __ldcs(p.rp_z + slot);
         u = __ldcs(p.rp_u + slot);
     } else {
+        const unsigned long long t = (unsigned long long)(h >> 1);
+        const unsigned batch = (unsigned)(h & 1);
         unsigned pl;
         double uz;
-        draw(p.seed, (unsigned long long)(p.id_base + batch * p.id_half_stride + i), (unsigned long long)t,
-             (unsigned)batch, p.nhalf, p.lemire_t, pl, uz, u);
-        j = (batch ? 0u : p.nhalf) + pl;               // :247 passive half
+        draw(p.keys, p.id_base[batch] + i, (unsigned)t, (unsigned)(t >> 32), batch, p.nhalf, p.lemire_t, pl, uz, u);
+        j = (batch ? 0u : p.nhalf) + pl;                 // :247 passive half
         const double s = dadd(dmul(uz, p.span), p.sia);  // :227
         z = dmul(s, s);
     }
 }
 
-// Owned-state accessors -------------------------------------------------------------------
-// Shared-memory layout of one CTA (SMEM=true), L = 2*per_cta local slots (half 0 then half 1):
-//   double xs[D][L]; double lps[L]; unsigned naccs[L];
-template <int D>
-struct SmemState {
-    double *xs, *lps;
-    unsigned *naccs;
-    unsigned L;
-    __device__ __forceinline__ SmemState(unsigned char *base, unsigned L_) : L(L_) {
-        xs = reinterpret_cast<double *>(base);
-        lps = xs + (size_t)D * L;
-        naccs = reinterpret_cast<unsigned *>(lps + L);
-    }
-    static __host__ __device__ size_t bytes(unsigned per_cta) { return (size_t)2 * per_cta * (8 * D + 8 + 4); }
+// The rare exact accept path: re-derive the accept uniform and evaluate the FP64 expression.
+template <bool REPLAY, bool SKIP_LOGZ>
+__device__ __forceinline__ bool accept_slow(const RunParams &p, long long h, unsigned i, double z, double p1, double p0) {
+    unsigned j;
+    double z2, u;
+    step_draws<REPLAY>(p, h, i, j, z2, u);
+    return accept_exact<SKIP_LOGZ>(p.nm1, z, p1, p0, u);
+}
+
+struct DrawRec {  // what a walker-step needs from its draws: 4 registers
+    unsigned j;   // partner (global index)
+    float q;      // accept-filter term, NaN = take the exact path
+    double z;
 };
 
-template <template <int> class Dn, int D, bool REPLAY, bool SMEM>
-__global__ void __launch_bounds__(block_threads<D>(), (D <= 4 ? 2 : 1)) emcee_run_kernel(const RunParams p, const Dn<D> dn) {
-    constexpr unsigned kBlock = block_threads<D>();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned tid = threadIdx.x;
+// Thinned chain store of one walker (:268-272): its current state right after its own update.
+template <int D>
+__device__ __forceinline__ void chain_store(const RunParams &p, size_t o, bool acc, const double (&y)[D],
+                                            const double (&xk)[D], double p1, double lpk) {
+    if (acc) store_row_cs<D>(p.chain_x + o * D, y);
+    else store_row_cs<D>(p.chain_x + o * D, xk);
+    __stcs(p.chain_lp + o, acc ? p1 : lpk);
+}
+
+// ------------------------------------------------------------------ general kernel
+// Owned state stays in L2/HBM; any ensemble size.  U walkers in flight per thread.
+template <template <int> class Dn, int D, bool REPLAY>
+__global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_kernel(const RunParams p,
+                                                                                    const Dn<D> dn) {
+    constexpr int U = in_flight<D>();
+    const unsigned tid = threadIdx.x, nthr = blockDim.x;
     const unsigned base = blockIdx.x * p.per_cta;  // first owned position (in each half)
     const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
-    SmemState<D> sm(smem_raw, 2 * p.per_cta);
 
-    if constexpr (SMEM) {  // stage the CTA's walkers of both halves
-        for (unsigned b = 0; b < 2; ++b)
-            for (unsigned l = tid; l < cnt; l += kBlock) {
-                const size_t k = (size_t)b * p.nhalf + base + l;
-                double v[D];
-                load_row<D>(p.x + k * D, v);
+    DrawRec dr[U];
+    auto make_draws = [&](long long h, unsigned l, DrawRec &r) {
+        unsigned j;
+        double z, u;
+        step_draws<REPLAY>(p, h, base + l, j, z, u);  // :250, :252, (:260 uniform)
+        r.j = j;
+        r.z = z;
+        r.q = filter_q<REPLAY>(p, z, u);
+    };
 #pragma unroll
-                for (int c = 0; c < D; ++c) sm.xs[c * sm.L + b * p.per_cta + l] = v[c];
-                sm.lps[b * p.per_cta + l] = p.lp[k];
-                sm.naccs[b * p.per_cta + l] = p.nacc[k];
-            }
-        // each thread only ever touches the slots it staged itself (same l stride): no sync needed
+    for (int q = 0; q < U; ++q) {
+        const unsigned l = tid + q * nthr;
+        if (l < cnt) make_draws(p.h0, l, dr[q]);
     }
 
     long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
     unsigned long long target = p.bar_base;
     for (long long h = p.h0; h < p.h1; ++h) {
-        const long long t = h >> 1;
         const int batch = (int)(h & 1);
         const bool store = (n > 0) && (phase == 0);  // :268  n>0 && rem(n,nthin)==0
         const unsigned a0 = batch ? p.nhalf : 0u;    // :247 active half
-        const unsigned sl0 = batch ? p.per_cta : 0u;
 
-        for (unsigned l = tid; l < cnt; l += kBlock) {
-            const unsigned i = base + l;
-            const size_t k = (size_t)a0 + i;
-            unsigned j;
-            double z, u;
-            step_draws<REPLAY>(p, t, batch, i, j, z, u);  // :250, :252
-            double xj[D], xk[D], y[D];
-            load_row_cg<D>(p.x + (size_t)j * D, xj);
-            double lpk;
-            if constexpr (SMEM) {
+        for (unsigned g = 0; g * nthr < cnt; g += U) {  // groups of U walkers in flight
+            if (g > 0) {
 #pragma unroll
-                for (int c = 0; c < D; ++c) xk[c] = sm.xs[c * sm.L + sl0 + l];
-                lpk = sm.lps[sl0 + l];
-            } else {
-                load_row<D>(p.x + k * D, xk);
-                lpk = p.lp[k];
+                for (int q = 0; q < U; ++q) {
+                    const unsigned l = tid + (g + q) * nthr;
+                    if (l < cnt) make_draws(h, l, dr[q]);
+                }
+            }
+            double xj[U][D], xk[U][D], lpk[U];
+#pragma unroll
+            for (int q = 0; q < U; ++q) {  // all gathers and owned rows of the group in flight together
+                const unsigned l = tid + (g + q) * nthr;
+                if (l < cnt) {
+                    const size_t k = (size_t)a0 + base + l;
+                    load_row_cg<D>(p.x + (size_t)dr[q].j * D, xj[q]);
+                    load_row<D>(p.x + k * D, xk[q]);
+                    lpk[q] = p.lp[k];
+                }
             }
 #pragma unroll
-            for (int c = 0; c < D; ++c) y[c] = dadd(xj[c], dmul(z, dsub(xk[c], xj[c])));  // :255
-            const double p1 = dn.logpdf(y);                                                // :257
-            const bool acc = accept_test<(D == 1 && !REPLAY)>(p, z, p1, lpk, u);           // :260
-            if (acc) {  // :261-265
-                store_row<D>(p.x + k * D, y);
-                if constexpr (SMEM) {
+            for (int q = 0; q < U; ++q) {
+                const unsigned l = tid + (g + q) * nthr;
+                if (l >= cnt) continue;
+                const size_t k = (size_t)a0 + base + l;
+                const double z = dr[q].z;
+                double y[D];
 #pragma unroll
-                    for (int c = 0; c < D; ++c) sm.xs[c * sm.L + sl0 + l] = y[c];
-                    sm.lps[sl0 + l] = p1;
-                    sm.naccs[sl0 + l] += 1u;
-                } else {
+                for (int c = 0; c < D; ++c) y[c] = dadd(xj[q][c], dmul(z, dsub(xk[q][c], xj[q][c])));  // :255
+                const double p1 = dn.logpdf(y);                                                          // :257
+                const double tt = (p1 - lpk[q]) + (double)dr[q].q * 0.6931471805599453;                  // :260
+                bool acc;
+                if (tt > (double)p.margin) acc = true;
+                else if (tt < -(double)p.margin) acc = false;
+                else acc = accept_slow<REPLAY, (D == 1 && !REPLAY)>(p, h, base + l, z, p1, lpk[q]);
+                if (acc) {  // :261-265
+                    store_row<D>(p.x + k * D, y);
                     p.lp[k] = p1;
                     p.nacc[k] += 1u;
                 }
-            }
-            if (store) {  // :268-272 -- the walker's current state, right after its own update
-                const size_t o = (size_t)sidx * p.nw + k;
-                if (acc) store_row_cs<D>(p.chain_x + o * D, y);
-                else store_row_cs<D>(p.chain_x + o * D, xk);
-                __stcs(p.chain_lp + o, acc ? p1 : lpk);
+                if (store) chain_store<D>(p, (size_t)sidx * p.nw + k, acc, y, xk[q], p1, lpk[q]);
             }
         }
         if (batch == 1) {
             if (n == 0) {  // :285-288 burn-in counters are discarded
-                for (unsigned l = tid; l < cnt; l += kBlock) {
-                    if constexpr (SMEM) {
-                        sm.naccs[l] = 0u;
-                        sm.naccs[p.per_cta + l] = 0u;
-                    } else {
-                        p.nacc[base + l] = 0u;
-                        p.nacc[(size_t)p.nhalf + base + l] = 0u;
-                    }
+                for (unsigned l = tid; l < cnt; l += nthr) {
+                    p.nacc[base + l] = 0u;
+                    p.nacc[(size_t)p.nhalf + base + l] = 0u;
                 }
             }
             if (store) ++sidx;
@@ -226,24 +243,141 @@ __global__ void __launch_bounds__(block_threads<D>(), (D <= 4 ? 2 : 1)) emcee_ru
         if (h + 1 < p.h1) {
             target += gridDim.x;
             __syncthreads();
+            if (gridDim.x > 1 && tid == 0) barrier_arrive(p.barrier);
+#pragma unroll
+            for (int q = 0; q < U; ++q) {  // next half-step's first group of draws, in the barrier's shadow
+                const unsigned l = tid + q * nthr;
+                if (l < cnt) make_draws(h + 1, l, dr[q]);
+            }
             if (gridDim.x > 1) {
-                if (tid == 0) {
-                    barrier_arrive(p.barrier);
-                    barrier_wait(p.barrier, target);
+                if (tid == 0) barrier_wait(p.barrier, target);
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ shared-memory-resident kernel
+// x / logp / accept counters of the CTA's walkers live in shared memory for the whole launch;
+// global x is only written on accept (so partners can gather it) and logp / counters are
+// written back once at the end.  Every thread owns at most kRounds walker positions of each
+// half: slot(half b, round q) = b*per_cta + q*blockDim + tid.  Layout (L = 2*per_cta slots),
+// component-major so that a warp's accesses are conflict-free:
+//   double xs[D][L]; double lps[L]; unsigned naccs[L];
+// Per half-step: the draws (Philox) of all rounds were made in the previous barrier's shadow;
+// partner rows are prefetched two rounds ahead.
+constexpr int kRounds = 4;
+constexpr int kSmemThreads = 448;
+
+template <template <int> class Dn, int D, bool REPLAY>
+__global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const unsigned tid = threadIdx.x, nthr = blockDim.x;
+    const unsigned base = blockIdx.x * p.per_cta;
+    const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
+    const unsigned L = 2 * p.per_cta;
+    const unsigned nv = cnt > tid ? (cnt - tid + nthr - 1) / nthr : 0u;  // rounds this thread owns (<= kRounds)
+    double *const xs = reinterpret_cast<double *>(smem_raw) + tid;
+    double *const lps = reinterpret_cast<double *>(smem_raw) + (size_t)D * L + tid;
+    unsigned *const nas = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(smem_raw) + (size_t)(D + 1) * L) + tid;
+
+    for (unsigned b = 0; b < 2; ++b)  // stage the owned walkers of both halves
+        for (unsigned q = 0; q < nv; ++q) {
+            const size_t k = (size_t)b * p.nhalf + base + tid + q * nthr;
+            const unsigned sl = b * p.per_cta + q * nthr;
+            double v[D];
+            load_row<D>(p.x + k * D, v);
+#pragma unroll
+            for (int c = 0; c < D; ++c) xs[c * L + sl] = v[c];
+            lps[sl] = p.lp[k];
+            nas[sl] = p.nacc[k];
+        }
+    // a thread only ever touches the slots it staged itself: no sync needed
+
+    DrawRec dr[kRounds];
+    auto make_draws = [&](long long h) {
+#pragma unroll
+        for (int q = 0; q < kRounds; ++q)
+            if (q < nv) {
+                unsigned j;
+                double z, u;
+                step_draws<REPLAY>(p, h, base + tid + q * nthr, j, z, u);  // :250, :252, (:260 uniform)
+                dr[q].j = j;
+                dr[q].z = z;
+                dr[q].q = filter_q<REPLAY>(p, z, u);
+            }
+    };
+    make_draws(p.h0);
+
+    long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
+    unsigned long long target = p.bar_base;
+    for (long long h = p.h0; h < p.h1; ++h) {
+        const unsigned batch = (unsigned)(h & 1);
+        const bool store = (n > 0) && (phase == 0);  // :268  n>0 && rem(n,nthin)==0
+        const unsigned hoff = batch ? p.per_cta : 0u;
+        const size_t k0 = (size_t)(batch ? p.nhalf : 0u) + base + tid;  // :247 active half, round 0
+        double *const xrow = p.x + k0 * D;
+
+        double xj[2][D];
+        if (0 < nv) load_row_cg<D>(p.x + (size_t)dr[0].j * D, xj[0]);
+        if (1 < nv) load_row_cg<D>(p.x + (size_t)dr[1].j * D, xj[1]);
+#pragma unroll
+        for (int q = 0; q < kRounds; ++q) {
+            if (q >= nv) break;
+            const unsigned sl = hoff + q * nthr;
+            double xk[D], y[D];
+#pragma unroll
+            for (int c = 0; c < D; ++c) xk[c] = xs[c * L + sl];
+            const double lpk = lps[sl];
+            const double z = dr[q].z;
+#pragma unroll
+            for (int c = 0; c < D; ++c) y[c] = dadd(xj[q & 1][c], dmul(z, dsub(xk[c], xj[q & 1][c])));  // :255
+            if (q + 2 < kRounds && q + 2 < nv)  // partner row two rounds ahead, before this round's stores
+                load_row_cg<D>(p.x + (size_t)dr[(q + 2) % kRounds].j * D, xj[q & 1]);
+            const double p1 = dn.logpdf(y);                                                // :257
+            const double tt = (p1 - lpk) + (double)dr[q].q * 0.6931471805599453;         // :260
+            bool acc;
+            if (tt > (double)p.margin) acc = true;
+            else if (tt < -(double)p.margin) acc = false;
+            else acc = accept_slow<REPLAY, (D == 1 && !REPLAY)>(p, h, base + tid + q * nthr, z, p1, lpk);
+            if (acc) {  // :261-265
+                store_row<D>(xrow + (size_t)q * nthr * D, y);
+#pragma unroll
+                for (int c = 0; c < D; ++c) xs[c * L + sl] = y[c];
+                lps[sl] = p1;
+                nas[sl] += 1u;
+            }
+            if (store) chain_store<D>(p, (size_t)sidx * p.nw + k0 + q * nthr, acc, y, xk, p1, lpk);
+        }
+        if (batch == 1) {
+            if (n == 0)  // :285-288 burn-in counters are discarded
+                for (unsigned q = 0; q < nv; ++q) {
+                    nas[q * nthr] = 0u;
+                    nas[p.per_cta + q * nthr] = 0u;
                 }
+            if (store) ++sidx;
+            ++n;
+            if (++phase == p.nthin) phase = 0;
+        }
+        if (h + 1 < p.h1) {
+            target += gridDim.x;
+            __syncthreads();
+            if (gridDim.x > 1 && tid == 0) barrier_arrive(p.barrier);
+            make_draws(h + 1);  // in the barrier's shadow: independent of the other CTAs
+            if (gridDim.x > 1) {
+                if (tid == 0) barrier_wait(p.barrier, target);
                 __syncthreads();
             }
         }
     }
 
-    if constexpr (SMEM) {  // write back what only lived in shared memory
-        for (unsigned b = 0; b < 2; ++b)
-            for (unsigned l = tid; l < cnt; l += kBlock) {
-                const size_t k = (size_t)b * p.nhalf + base + l;
-                p.lp[k] = sm.lps[b * p.per_cta + l];
-                p.nacc[k] = sm.naccs[b * p.per_cta + l];
-            }
-    }
+    for (unsigned b = 0; b < 2; ++b)  // write back what only lived in shared memory
+        for (unsigned q = 0; q < nv; ++q) {
+            const size_t k = (size_t)b * p.nhalf + base + tid + q * nthr;
+            const unsigned sl = b * p.per_cta + q * nthr;
+            p.lp[k] = lps[sl];
+            p.nacc[k] = nas[sl];
+        }
 }
 
 // K4: batched log-density (initial p0s, src/samplers.jl:209; make_theta0s, :334-338).
