@@ -267,11 +267,18 @@ def main():
     out_ar = torch.empty((nw,), dtype=torch.float64).pin_memory()
 
     def e2e_step(step):
+        ta = time.perf_counter()
         s = km.Sampler(ld, x0_pinned.numpy(), nitw, nbw, nthin, 2.0, seed=(step << 8) | rank,
                        walker_id_base=rank * nw, launch_mode=args.launch_mode)
+        tb = time.perf_counter()
         s.run(-1)
+        tc = time.perf_counter()
         s.results(out_th.numpy(), out_lp.numpy(), out_ar.numpy())
+        td = time.perf_counter()
         s.close()
+        if os.environ.get("KMC_BENCH_VERBOSE"):
+            print(f"e2e step {step}: create {1e3 * (tb - ta):.1f} run {1e3 * (tc - tb):.1f} results "
+                  f"{1e3 * (td - tc):.1f} close {1e3 * (time.perf_counter() - td):.1f} ms", file=sys.stderr)
 
     e2e_steps = max(1, min(args.steps, 3))
     e2e_step(0)

@@ -63,6 +63,8 @@ typedef struct kmc_emcee_opts {
 int32_t kmc_version(void);
 const char *kmc_last_error(void);
 int32_t kmc_device_count(int32_t *count);
+/* Device buffers of destroyed samplers are cached for reuse; this releases them to the driver. */
+int32_t kmc_trim(void);
 
 /* Log-density plugin registry: replaces the user closure `pdf` (src/samplers.jl:257,:209).
  *   "exponential"  README.md:15             params: none

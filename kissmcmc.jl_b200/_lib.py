@@ -15,7 +15,7 @@ MODE_PHILOX, MODE_REPLAY = 0, 1
 
 # every symbol include/kissmcmc_cuda.h declares
 SYMBOLS = [
-    "kmc_version", "kmc_last_error", "kmc_device_count",
+    "kmc_version", "kmc_last_error", "kmc_device_count", "kmc_trim",
     "kmc_density_create", "kmc_density_destroy", "kmc_density_eval",
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
     "kmc_emcee_run", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",

@@ -8,6 +8,8 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,6 +37,69 @@ int32_t fail(int32_t code, const char *fmt, ...) {
             return fail(KMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
                         __FILE__, __LINE__);                                                    \
     } while (0)
+
+// ------------------------------------------------------------------ device memory cache
+// cudaMalloc / cudaFree cost milliseconds once pinned host memory and other contexts are
+// mapped; samplers are created and destroyed per emcee() call, so freed blocks are kept in a
+// small per-device cache and reused by exact size.  kmc_trim() releases them.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void *> free_blocks;  // (device, bytes) -> ptr
+    std::map<void *, std::pair<int, size_t>> live;
+    size_t cached_bytes = 0;
+    static constexpr size_t kMaxCached = (size_t)8 << 30;
+} g_cache;
+
+cudaError_t dev_alloc(void **out, size_t bytes, int device) {
+    {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        auto it = g_cache.free_blocks.find({device, bytes});
+        if (it != g_cache.free_blocks.end()) {
+            *out = it->second;
+            g_cache.free_blocks.erase(it);
+            g_cache.cached_bytes -= bytes;
+            g_cache.live[*out] = {device, bytes};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e != cudaSuccess) {  // give cached blocks back and retry once
+        cudaGetLastError();
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        for (auto &kv : g_cache.free_blocks) cudaFree(kv.second);
+        g_cache.free_blocks.clear();
+        g_cache.cached_bytes = 0;
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess) {
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.live[*out] = {device, bytes};
+    }
+    return e;
+}
+
+template <typename T>
+cudaError_t dev_alloc(T **out, size_t bytes, int device) {
+    return dev_alloc(reinterpret_cast<void **>(out), bytes, device);
+}
+
+void dev_free(void *p) {
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    auto it = g_cache.live.find(p);
+    if (it == g_cache.live.end()) {
+        cudaFree(p);
+        return;
+    }
+    const auto key = it->second;
+    g_cache.live.erase(it);
+    if (g_cache.cached_bytes + key.second > DevCache::kMaxCached) {
+        cudaFree(p);
+        return;
+    }
+    g_cache.free_blocks.insert({key, p});
+    g_cache.cached_bytes += key.second;
+}
 
 // ------------------------------------------------------------------ kernel registry
 struct Ops {
@@ -160,6 +225,17 @@ int32_t kmc_device_count(int32_t *count) {
     return KMC_OK;
 }
 
+int32_t kmc_trim(void) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    for (auto &kv : g_cache.free_blocks) {
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second);
+    }
+    g_cache.free_blocks.clear();
+    g_cache.cached_bytes = 0;
+    return KMC_OK;
+}
+
 int32_t kmc_density_create(const char *name, int32_t d, const double *params, int64_t nparams,
                            const void *data, int64_t data_bytes, int32_t device,
                            kmc_density_t *out) {
@@ -202,8 +278,8 @@ int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, doub
     if (nw == 0) return KMC_OK;
     CU_TRY(cudaSetDevice(h->device));
     double *dx = nullptr, *dl = nullptr;
-    CU_TRY(cudaMalloc(&dx, sizeof(double) * nw * h->d));
-    cudaError_t e = cudaMalloc(&dl, sizeof(double) * nw);
+    CU_TRY(dev_alloc(&dx, sizeof(double) * nw * h->d, h->device));
+    cudaError_t e = dev_alloc(&dl, sizeof(double) * nw, h->device);
     if (e == cudaSuccess) e = cudaMemcpy(dx, thetas, sizeof(double) * nw * h->d, cudaMemcpyHostToDevice);
     if (e == cudaSuccess) {
         long long nwl = nw;
@@ -211,8 +287,8 @@ int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, doub
         e = cudaLaunchKernel(h->ops.eval, dim3((unsigned)((nw + 255) / 256)), dim3(256), args, 0, nullptr);
     }
     if (e == cudaSuccess) e = cudaMemcpy(logp_out, dl, sizeof(double) * nw, cudaMemcpyDeviceToHost);
-    cudaFree(dx);
-    cudaFree(dl);
+    dev_free(dx);
+    dev_free(dl);
     if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "density eval failed: %s", cudaGetErrorString(e));
     return KMC_OK;
 }
@@ -220,16 +296,17 @@ int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, doub
 int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     if (!s) return KMC_OK;
     cudaSetDevice(s->opts.device);
-    cudaFree(s->x);
-    cudaFree(s->lp);
-    cudaFree(s->chain_x);
-    cudaFree(s->chain_lp);
-    cudaFree(s->nacc);
-    cudaFree(s->barrier);
-    cudaFree(s->rp_partner);
-    cudaFree(s->rp_z);
-    cudaFree(s->rp_u);
-    cudaFree(s->scratch);
+    if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks must be idle before reuse
+    dev_free(s->x);
+    dev_free(s->lp);
+    dev_free(s->chain_x);
+    dev_free(s->chain_lp);
+    dev_free(s->nacc);
+    dev_free(s->barrier);
+    dev_free(s->rp_partner);
+    dev_free(s->rp_z);
+    dev_free(s->rp_u);
+    dev_free(s->scratch);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -281,14 +358,14 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     s->stream = s->own_stream;
     CU_TRY_S(cudaEventCreate(&s->ev0));
     CU_TRY_S(cudaEventCreate(&s->ev1));
-    CU_TRY_S(cudaMalloc(&s->x, sizeof(double) * s->nw * d));
-    CU_TRY_S(cudaMalloc(&s->lp, sizeof(double) * s->nw));
-    CU_TRY_S(cudaMalloc(&s->nacc, sizeof(unsigned) * s->nw));
-    CU_TRY_S(cudaMalloc(&s->barrier, sizeof(unsigned long long)));
-    CU_TRY_S(cudaMalloc(&s->scratch, 4 * sizeof(unsigned long long)));
+    CU_TRY_S(dev_alloc(&s->x, sizeof(double) * s->nw * d, opts->device));
+    CU_TRY_S(dev_alloc(&s->lp, sizeof(double) * s->nw, opts->device));
+    CU_TRY_S(dev_alloc(&s->nacc, sizeof(unsigned) * s->nw, opts->device));
+    CU_TRY_S(dev_alloc(&s->barrier, sizeof(unsigned long long), opts->device));
+    CU_TRY_S(dev_alloc(&s->scratch, 4 * sizeof(unsigned long long), opts->device));
     if (s->ns > 0) {
-        CU_TRY_S(cudaMalloc(&s->chain_x, sizeof(double) * s->ns * s->nw * d));
-        CU_TRY_S(cudaMalloc(&s->chain_lp, sizeof(double) * s->ns * s->nw));
+        CU_TRY_S(dev_alloc(&s->chain_x, sizeof(double) * s->ns * s->nw * d, opts->device));
+        CU_TRY_S(dev_alloc(&s->chain_lp, sizeof(double) * s->ns * s->nw, opts->device));
     }
     CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nw, s->stream));
     CU_TRY_S(cudaMemsetAsync(s->barrier, 0, sizeof(unsigned long long), s->stream));
@@ -361,16 +438,16 @@ int32_t kmc_emcee_set_replay(kmc_sampler_t s, const int64_t *partner, const doub
         if (partner[i] < 0 || partner[i] >= s->nw)
             return fail(KMC_ERR_INVALID, "replay partner %lld at slot %lld is outside [0, nwalkers)",
                         (long long)partner[i], i);
-    cudaFree(s->rp_partner);
-    cudaFree(s->rp_z);
-    cudaFree(s->rp_u);
+    dev_free(s->rp_partner);
+    dev_free(s->rp_z);
+    dev_free(s->rp_u);
     s->rp_partner = nullptr;
     s->rp_z = s->rp_u = nullptr;
     s->rp_niters = 0;
     if (n > 0) {
-        CU_TRY(cudaMalloc(&s->rp_partner, sizeof(long long) * n));
-        CU_TRY(cudaMalloc(&s->rp_z, sizeof(double) * n));
-        CU_TRY(cudaMalloc(&s->rp_u, sizeof(double) * n));
+        CU_TRY(dev_alloc(&s->rp_partner, sizeof(long long) * n, s->opts.device));
+        CU_TRY(dev_alloc(&s->rp_z, sizeof(double) * n, s->opts.device));
+        CU_TRY(dev_alloc(&s->rp_u, sizeof(double) * n, s->opts.device));
         CU_TRY(cudaMemcpy(s->rp_partner, partner, sizeof(long long) * n, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(s->rp_z, z, sizeof(double) * n, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(s->rp_u, u, sizeof(double) * n, cudaMemcpyHostToDevice));
@@ -525,7 +602,7 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
         long long wc = std::max<long long>(32, (64LL << 20) / (sizeof(double) * ns * d));
         wc = std::min(wc, nw);
         double *stage = nullptr;
-        CU_TRY(cudaMalloc(&stage, sizeof(double) * wc * ns * d));
+        CU_TRY(dev_alloc(&stage, sizeof(double) * wc * ns * d, s->opts.device));
         cudaError_t e = cudaSuccess;
         for (long long w0 = 0; w0 < nw && e == cudaSuccess; w0 += wc) {
             const long long cur = std::min(wc, nw - w0);
@@ -546,7 +623,7 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
         }
         if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
         if (e == cudaSuccess) e = cudaGetLastError();
-        cudaFree(stage);
+        dev_free(stage);
         if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "copy_results failed: %s", cudaGetErrorString(e));
     }
     if (accept_ratio) {

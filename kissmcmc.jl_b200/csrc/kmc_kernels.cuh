@@ -269,28 +269,54 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
 constexpr int kRounds = 4;
 constexpr int kSmemThreads = 448;
 
+// Shared memory through explicit 32-bit addresses: every access is (per-thread base) +
+// (warp-uniform offset), so a thread keeps ONE address register for all of its slots.
+__device__ __forceinline__ double lds_f64(unsigned a) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned a, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ unsigned lds_u32(unsigned a) {
+    unsigned v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+
 template <template <int> class Dn, int D, bool REPLAY>
 __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const unsigned tid = threadIdx.x, nthr = blockDim.x;
-    const unsigned base = blockIdx.x * p.per_cta;
-    const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
+    const unsigned nthr = blockDim.x;
     const unsigned L = 2 * p.per_cta;
-    const unsigned nv = cnt > tid ? (cnt - tid + nthr - 1) / nthr : 0u;  // rounds this thread owns (<= kRounds)
-    double *const xs = reinterpret_cast<double *>(smem_raw) + tid;
-    double *const lps = reinterpret_cast<double *>(smem_raw) + (size_t)D * L + tid;
-    unsigned *const nas = reinterpret_cast<unsigned *>(reinterpret_cast<double *>(smem_raw) + (size_t)(D + 1) * L) + tid;
+    // ---- the per-thread registers that live across the whole launch -------------------
+    const unsigned wid = blockIdx.x * p.per_cta + threadIdx.x;  // owned position of round 0 (in each half)
+    const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw) + 8u * threadIdx.x;  // xs/lps slot of round 0
+    const unsigned nbase = (unsigned)__cvta_generic_to_shared(smem_raw) + 8u * (D + 1) * L + 4u * threadIdx.x;
+    double *const grow = p.x + (size_t)wid * D;  // own global row of (half 0, round 0)
+    unsigned nv;                                 // rounds this thread owns (<= kRounds)
+    {
+        const unsigned base = blockIdx.x * p.per_cta;
+        const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
+        nv = cnt > threadIdx.x ? (cnt - threadIdx.x + nthr - 1) / nthr : 0u;
+    }
+    // slot(half b, round q) = b*per_cta + q*nthr (+ tid, folded into the bases); byte offsets
+    // of x component c: 8*(c*L + slot), logp: 8*(D*L + slot), counter: 4*slot  -- all warp-uniform
 
     for (unsigned b = 0; b < 2; ++b)  // stage the owned walkers of both halves
         for (unsigned q = 0; q < nv; ++q) {
-            const size_t k = (size_t)b * p.nhalf + base + tid + q * nthr;
+            const size_t ro = (size_t)b * p.nhalf + (size_t)q * nthr;
             const unsigned sl = b * p.per_cta + q * nthr;
             double v[D];
-            load_row<D>(p.x + k * D, v);
+            load_row<D>(grow + ro * D, v);
 #pragma unroll
-            for (int c = 0; c < D; ++c) xs[c * L + sl] = v[c];
-            lps[sl] = p.lp[k];
-            nas[sl] = p.nacc[k];
+            for (int c = 0; c < D; ++c) sts_f64(sbase + 8u * (c * L + sl), v[c]);
+            sts_f64(sbase + 8u * (D * L + sl), p.lp[wid + ro]);
+            sts_u32(nbase + 4u * sl, p.nacc[wid + ro]);
         }
     // a thread only ever touches the slots it staged itself: no sync needed
 
@@ -301,7 +327,7 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
             if (q < nv) {
                 unsigned j;
                 double z, u;
-                step_draws<REPLAY>(p, h, base + tid + q * nthr, j, z, u);  // :250, :252, (:260 uniform)
+                step_draws<REPLAY>(p, h, wid + q * nthr, j, z, u);  // :250, :252, (:260 uniform)
                 dr[q].j = j;
                 dr[q].z = z;
                 dr[q].q = filter_q<REPLAY>(p, z, u);
@@ -309,14 +335,18 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
     };
     make_draws(p.h0);
 
-    long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
+    // launch-local 32-bit bookkeeping of the reference's n (:245), rem(n, nthin) and the sample index
+    const unsigned nh = (unsigned)(p.h1 - p.h0);
+    long long n = p.n0;
+    unsigned phase = (unsigned)p.phase0;
+    long long sidx = p.sidx0;
     unsigned long long target = p.bar_base;
-    for (long long h = p.h0; h < p.h1; ++h) {
+    for (unsigned hh = 0; hh < nh; ++hh) {
+        const long long h = p.h0 + hh;
         const unsigned batch = (unsigned)(h & 1);
         const bool store = (n > 0) && (phase == 0);  // :268  n>0 && rem(n,nthin)==0
-        const unsigned hoff = batch ? p.per_cta : 0u;
-        const size_t k0 = (size_t)(batch ? p.nhalf : 0u) + base + tid;  // :247 active half, round 0
-        double *const xrow = p.x + k0 * D;
+        const unsigned hslot = batch ? p.per_cta : 0u;            // first slot of the active half
+        const size_t hrow = batch ? (size_t)p.nhalf : (size_t)0;  // first global row of the active half (:247)
 
         double xj[2][D];
         if (0 < nv) load_row_cg<D>(p.x + (size_t)dr[0].j * D, xj[0]);
@@ -324,48 +354,49 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
 #pragma unroll
         for (int q = 0; q < kRounds; ++q) {
             if (q >= nv) break;
-            const unsigned sl = hoff + q * nthr;
+            const unsigned sl = hslot + q * nthr;      // warp-uniform
+            const size_t ro = hrow + (size_t)q * nthr;  // warp-uniform
             double xk[D], y[D];
 #pragma unroll
-            for (int c = 0; c < D; ++c) xk[c] = xs[c * L + sl];
-            const double lpk = lps[sl];
+            for (int c = 0; c < D; ++c) xk[c] = lds_f64(sbase + 8u * (c * L + sl));
+            const double lpk = lds_f64(sbase + 8u * (D * L + sl));
             const double z = dr[q].z;
 #pragma unroll
             for (int c = 0; c < D; ++c) y[c] = dadd(xj[q & 1][c], dmul(z, dsub(xk[c], xj[q & 1][c])));  // :255
             if (q + 2 < kRounds && q + 2 < nv)  // partner row two rounds ahead, before this round's stores
                 load_row_cg<D>(p.x + (size_t)dr[(q + 2) % kRounds].j * D, xj[q & 1]);
-            const double p1 = dn.logpdf(y);                                                // :257
-            const double tt = (p1 - lpk) + (double)dr[q].q * 0.6931471805599453;         // :260
+            const double p1 = dn.logpdf(y);                                        // :257
+            const double tt = (p1 - lpk) + (double)dr[q].q * 0.6931471805599453;  // :260
             bool acc;
             if (tt > (double)p.margin) acc = true;
             else if (tt < -(double)p.margin) acc = false;
-            else acc = accept_slow<REPLAY, (D == 1 && !REPLAY)>(p, h, base + tid + q * nthr, z, p1, lpk);
+            else acc = accept_slow<REPLAY, (D == 1 && !REPLAY)>(p, h, wid + q * nthr, z, p1, lpk);
             if (acc) {  // :261-265
-                store_row<D>(xrow + (size_t)q * nthr * D, y);
+                store_row<D>(grow + ro * D, y);
 #pragma unroll
-                for (int c = 0; c < D; ++c) xs[c * L + sl] = y[c];
-                lps[sl] = p1;
-                nas[sl] += 1u;
+                for (int c = 0; c < D; ++c) sts_f64(sbase + 8u * (c * L + sl), y[c]);
+                sts_f64(sbase + 8u * (D * L + sl), p1);
+                sts_u32(nbase + 4u * sl, lds_u32(nbase + 4u * sl) + 1u);
             }
-            if (store) chain_store<D>(p, (size_t)sidx * p.nw + k0 + q * nthr, acc, y, xk, p1, lpk);
+            if (store) chain_store<D>(p, (size_t)sidx * p.nw + wid + ro, acc, y, xk, p1, lpk);
         }
         if (batch == 1) {
             if (n == 0)  // :285-288 burn-in counters are discarded
                 for (unsigned q = 0; q < nv; ++q) {
-                    nas[q * nthr] = 0u;
-                    nas[p.per_cta + q * nthr] = 0u;
+                    sts_u32(nbase + 4u * (q * nthr), 0u);
+                    sts_u32(nbase + 4u * (p.per_cta + q * nthr), 0u);
                 }
             if (store) ++sidx;
             ++n;
-            if (++phase == p.nthin) phase = 0;
+            if (++phase == (unsigned)p.nthin) phase = 0;
         }
-        if (h + 1 < p.h1) {
+        if (hh + 1 < nh) {
             target += gridDim.x;
             __syncthreads();
-            if (gridDim.x > 1 && tid == 0) barrier_arrive(p.barrier);
+            if (gridDim.x > 1 && threadIdx.x == 0) barrier_arrive(p.barrier);
             make_draws(h + 1);  // in the barrier's shadow: independent of the other CTAs
             if (gridDim.x > 1) {
-                if (tid == 0) barrier_wait(p.barrier, target);
+                if (threadIdx.x == 0) barrier_wait(p.barrier, target);
                 __syncthreads();
             }
         }
@@ -373,10 +404,10 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
 
     for (unsigned b = 0; b < 2; ++b)  // write back what only lived in shared memory
         for (unsigned q = 0; q < nv; ++q) {
-            const size_t k = (size_t)b * p.nhalf + base + tid + q * nthr;
+            const size_t ro = (size_t)b * p.nhalf + (size_t)q * nthr;
             const unsigned sl = b * p.per_cta + q * nthr;
-            p.lp[k] = lps[sl];
-            p.nacc[k] = nas[sl];
+            p.lp[wid + ro] = lds_f64(sbase + 8u * (D * L + sl));
+            p.nacc[wid + ro] = lds_u32(nbase + 4u * sl);
         }
 }
 

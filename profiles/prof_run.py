@@ -1,5 +1,5 @@
 """Small driver for ncu captures: runs a few iterations of a bench workload.
-    python profiles/prof_run.py [workload] [iters] [launch_mode]"""
+    python profiles/prof_run.py [workload] [iters] [launch_mode] [nwalkers]"""
 import sys
 from pathlib import Path
 
@@ -10,6 +10,8 @@ import kissmcmc_b200 as km  # noqa: E402
 wl = bench.WORKLOADS[sys.argv[1] if len(sys.argv) > 1 else "rosenbrock2d"]
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+if len(sys.argv) > 4:
+    wl = dict(wl, nw=int(sys.argv[4]))
 params, x0 = bench.make_inputs(wl, 1)
 ld = km.LogDensity(wl["plugin"], wl["d"], params)
 for rep in range(3):
