@@ -57,6 +57,13 @@ typedef struct kmc_emcee_opts {
     int32_t launch_mode;    /* 0 = persistent kernel, grid barrier between half-steps (default);
                                1 = one launch per half-step */
     int32_t reserved;
+    /* Sharded ensemble (one ensemble over several GPUs): this sampler holds
+     * the FULL ensemble's positions but updates only positions [shard_begin, shard_begin +
+     * shard_count) of each half; the caller makes the updated slices of the other shards visible
+     * between half-steps (all-gather).  shard_count = 0: the whole half (single GPU).  Draws are
+     * keyed by the global walker index, so a sharded run reproduces the single-GPU run exactly. */
+    int64_t shard_begin;
+    int64_t shard_count;
 } kmc_emcee_opts;
 
 /* Library / device ------------------------------------------------------------------- */
@@ -101,7 +108,13 @@ int32_t kmc_emcee_set_replay(kmc_sampler_t s, const int64_t *partner, const doub
 /* Advance `niters` outer iterations (niters < 0: all that remain).  Asynchronous on the
  * sampler's stream. */
 int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters);
+/* Advance `nhalfsteps` half-ensemble sweeps (:246-273); two per outer iteration.  A sharded
+ * run alternates kmc_emcee_run_half(s, 1) with the exchange of the just-updated half. */
+int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps);
 int32_t kmc_emcee_sync(kmc_sampler_t s);
+/* Device pointers of the ensemble state (x: [nw][d] FP64, logp: [nw] FP64, naccept: [nw] u32),
+ * valid until kmc_emcee_destroy; for stream-ordered exchanges by the caller. */
+int32_t kmc_emcee_device_ptrs(kmc_sampler_t s, void **x, void **logp, void **naccept);
 /* Device time of the kernels launched by the last kmc_emcee_run (CUDA events on the launch
  * stream) and how many kernels that was.  Synchronises. */
 int32_t kmc_emcee_last_run_ms(kmc_sampler_t s, double *ms, int64_t *launches);
@@ -110,7 +123,10 @@ int32_t kmc_emcee_last_run_ms(kmc_sampler_t s, double *ms, int64_t *launches);
 int32_t kmc_emcee_progress(kmc_sampler_t s, int64_t *iters_done, double *naccept_mean,
                            double *naccept_std, int64_t *outliers);
 int32_t kmc_emcee_nsamples(kmc_sampler_t s, int64_t *ns);
-/* Results (:291-292).  thetas [nw][ns][d], logp [nw][ns], accept_ratio [nw]; any may be NULL. */
+/* Walkers this sampler stores chains for: nwalkers, or 2*shard_count when sharded. */
+int32_t kmc_emcee_nlocal(kmc_sampler_t s, int64_t *nl);
+/* Results (:291-292).  thetas [nl][ns][d], logp [nl][ns], accept_ratio [nl]; any may be NULL.
+ * nl = nwalkers, or 2*shard_count for a sharded sampler (its slice of half 0, then of half 1). */
 int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp,
                                double *accept_ratio);
 /* Current ensemble: theta [nw][d], logp [nw], naccept [nw]; any may be NULL. */

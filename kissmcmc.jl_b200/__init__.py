@@ -9,7 +9,10 @@ from ._lib import KmcError, MODE_PHILOX, MODE_REPLAY, SYMBOLS, LIB_PATH, device_
 from .api import (LogDensity, Sampler, ball_randn, emcee, exponential, gaussian, gaussian_params, lognormal,
                   make_theta0s, philox4x32_10, rosenbrock, squash_walkers)
 
+from . import distributed  # noqa: E402  (multi-GPU drivers; imports torch)
+
 __all__ = [
+    "distributed",
     "emcee", "make_theta0s", "squash_walkers", "LogDensity", "Sampler", "exponential", "rosenbrock", "gaussian",
     "gaussian_params", "lognormal", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "ball_randn",
     "philox4x32_10", "SYMBOLS", "LIB_PATH", "lib",

@@ -18,7 +18,7 @@ SYMBOLS = [
     "kmc_version", "kmc_last_error", "kmc_device_count", "kmc_trim",
     "kmc_density_create", "kmc_density_destroy", "kmc_density_eval",
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
-    "kmc_emcee_run", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
+    "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
     "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state",
 ]
 
@@ -34,6 +34,7 @@ class EmceeOpts(C.Structure):
         ("niter_walker", C.c_int64), ("nburnin_walker", C.c_int64), ("nthin", C.c_int64),
         ("a_scale", C.c_double), ("seed", C.c_uint64), ("mode", C.c_int32), ("device", C.c_int32),
         ("walker_id_base", C.c_int64), ("launch_mode", C.c_int32), ("reserved", C.c_int32),
+        ("shard_begin", C.c_int64), ("shard_count", C.c_int64),
     ]
 
 
@@ -60,6 +61,9 @@ lib.kmc_emcee_set_stream.argtypes = [C.c_void_p, C.c_void_p]
 lib.kmc_emcee_set_replay.argtypes = [C.c_void_p, _i64p, _dp, _dp, C.c_int64]
 lib.kmc_emcee_run.argtypes = [C.c_void_p, C.c_int64]
 lib.kmc_emcee_sync.argtypes = [C.c_void_p]
+lib.kmc_emcee_run_half.argtypes = [C.c_void_p, C.c_int64]
+lib.kmc_emcee_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
+lib.kmc_emcee_nlocal.argtypes = [C.c_void_p, _i64p]
 lib.kmc_emcee_last_run_ms.argtypes = [C.c_void_p, _dp, _i64p]
 lib.kmc_emcee_progress.argtypes = [C.c_void_p, _i64p, _dp, _dp, _i64p]
 lib.kmc_emcee_nsamples.argtypes = [C.c_void_p, _i64p]

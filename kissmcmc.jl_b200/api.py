@@ -109,7 +109,7 @@ class Sampler:
     """Owns a kmc_sampler_t.  Counts are PER WALKER (niter_walker = niter // nwalkers)."""
 
     def __init__(self, logdensity: LogDensity, theta0s, niter_walker, nburnin_walker, nthin=1, a_scale=2.0,
-                 seed=0, mode=MODE_PHILOX, device=None, walker_id_base=0, launch_mode=0):
+                 seed=0, mode=MODE_PHILOX, device=None, walker_id_base=0, launch_mode=0, shard=None):
         x = np.ascontiguousarray(np.asarray(theta0s, dtype=np.float64))
         if x.ndim == 1:
             x = x.reshape(-1, 1)
@@ -117,13 +117,16 @@ class Sampler:
         self.logdensity = logdensity
         self.opts = EmceeOpts(int(niter_walker), int(nburnin_walker), int(nthin), float(a_scale), int(seed),
                               int(mode), int(logdensity.device if device is None else device),
-                              int(walker_id_base), int(launch_mode), 0)
+                              int(walker_id_base), int(launch_mode), 0,
+                              int(shard[0]) if shard else 0, int(shard[1]) if shard else 0)
         h = C.c_void_p()
         check(lib.kmc_emcee_create(logdensity._h, _ptr(x), self.nw, self.d, C.byref(self.opts), C.byref(h)))
         self._h = h
         n = C.c_int64()
         check(lib.kmc_emcee_nsamples(h, C.byref(n)))
         self.ns = n.value
+        check(lib.kmc_emcee_nlocal(h, C.byref(n)))
+        self.nl = n.value            # walkers whose chains this sampler stores (2*shard_count if sharded)
 
     def close(self):
         h, self._h = getattr(self, "_h", None), None
@@ -148,8 +151,20 @@ class Sampler:
         if sync:
             check(lib.kmc_emcee_sync(self._h))
 
+    def run_half(self, nhalfsteps: int = 1, sync: bool = False):
+        """Advance half-ensemble sweeps (two per outer iteration); asynchronous by default."""
+        check(lib.kmc_emcee_run_half(self._h, int(nhalfsteps)))
+        if sync:
+            check(lib.kmc_emcee_sync(self._h))
+
     def sync(self):
         check(lib.kmc_emcee_sync(self._h))
+
+    def device_ptrs(self):
+        """(x, logp, naccept) device addresses: x [nw][d] f64, logp [nw] f64, naccept [nw] u32."""
+        x, lp, na = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        check(lib.kmc_emcee_device_ptrs(self._h, C.byref(x), C.byref(lp), C.byref(na)))
+        return x.value, lp.value, na.value
 
     def last_run_ms(self):
         ms, n = C.c_double(), C.c_int64()
@@ -162,9 +177,9 @@ class Sampler:
         return it.value, mean.value, sd.value, outl.value
 
     def results(self, out_thetas=None, out_logp=None, out_ratio=None):
-        th = np.empty((self.nw, self.ns, self.d)) if out_thetas is None else out_thetas
-        lp = np.empty((self.nw, self.ns)) if out_logp is None else out_logp
-        ar = np.empty(self.nw) if out_ratio is None else out_ratio
+        th = np.empty((self.nl, self.ns, self.d)) if out_thetas is None else out_thetas
+        lp = np.empty((self.nl, self.ns)) if out_logp is None else out_logp
+        ar = np.empty(self.nl) if out_ratio is None else out_ratio
         check(lib.kmc_emcee_copy_results(self._h, _ptr(th), _ptr(lp), _ptr(ar)))
         return th, lp, ar
 

@@ -188,7 +188,9 @@ struct kmc_sampler_s {
     kmc_emcee_opts opts{};
     long long nw = 0, nhalf = 0, ns = 0;
     int d = 0;
-    long long iters_done = 0;  // outer iterations completed (t)
+    long long hdone = 0;       // half-steps completed (2 per outer iteration)
+    long long sbeg = 0, scnt = 0;  // shard: positions of each half this sampler updates
+    long long nl = 0;          // walkers this sampler stores chains for (2*scnt)
     double *x = nullptr, *lp = nullptr, *chain_x = nullptr, *chain_lp = nullptr;
     unsigned *nacc = nullptr;
     unsigned long long *barrier = nullptr;
@@ -339,6 +341,14 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     s->nw = nwalkers;
     s->nhalf = nwalkers / 2;
     s->d = d;
+    s->sbeg = opts->shard_count > 0 ? opts->shard_begin : 0;
+    s->scnt = opts->shard_count > 0 ? opts->shard_count : s->nhalf;
+    s->nl = 2 * s->scnt;
+    if (s->sbeg < 0 || s->sbeg + s->scnt > s->nhalf) {
+        delete s;
+        return fail(KMC_ERR_INVALID, "shard [%lld, %lld) is outside the half-ensemble [0, %lld)", s->sbeg,
+                    s->sbeg + s->scnt, (long long)(nwalkers / 2));
+    }
     const long long nspan = opts->niter_walker - opts->nburnin_walker;
     s->ns = nspan > 0 ? nspan / opts->nthin : 0;  // :234
 
@@ -364,8 +374,8 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     CU_TRY_S(dev_alloc(&s->barrier, sizeof(unsigned long long), opts->device));
     CU_TRY_S(dev_alloc(&s->scratch, 4 * sizeof(unsigned long long), opts->device));
     if (s->ns > 0) {
-        CU_TRY_S(dev_alloc(&s->chain_x, sizeof(double) * s->ns * s->nw * d, opts->device));
-        CU_TRY_S(dev_alloc(&s->chain_lp, sizeof(double) * s->ns * s->nw, opts->device));
+        CU_TRY_S(dev_alloc(&s->chain_x, sizeof(double) * s->ns * s->nl * d, opts->device));
+        CU_TRY_S(dev_alloc(&s->chain_lp, sizeof(double) * s->ns * s->nl, opts->device));
     }
     CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nw, s->stream));
     CU_TRY_S(cudaMemsetAsync(s->barrier, 0, sizeof(unsigned long long), s->stream));
@@ -381,10 +391,10 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
         auto geometry = [&](const void *kern, int maxblk, int ctas_per_sm, size_t smem_per_walker, bool &fits) {
-            const long long want = (s->nhalf + maxblk - 1) / maxblk;
+            const long long want = (s->scnt + maxblk - 1) / maxblk;
             s->grid = (unsigned)std::min<long long>(want, (long long)ctas_per_sm * s->nsm);
-            s->per_cta = (unsigned)((s->nhalf + s->grid - 1) / s->grid);
-            s->grid = (unsigned)((s->nhalf + s->per_cta - 1) / s->per_cta);
+            s->per_cta = (unsigned)((s->scnt + s->grid - 1) / s->grid);
+            s->grid = (unsigned)((s->scnt + s->per_cta - 1) / s->per_cta);
             const unsigned rounds = (s->per_cta + maxblk - 1) / maxblk;
             s->block = std::min<unsigned>(maxblk, (((s->per_cta + rounds - 1) / rounds + 31) / 32) * 32);
             s->smem_bytes = (size_t)2 * s->per_cta * smem_per_walker;
@@ -452,22 +462,23 @@ int32_t kmc_emcee_set_replay(kmc_sampler_t s, const int64_t *partner, const doub
         CU_TRY(cudaMemcpy(s->rp_z, z, sizeof(double) * n, cudaMemcpyHostToDevice));
         CU_TRY(cudaMemcpy(s->rp_u, u, sizeof(double) * n, cudaMemcpyHostToDevice));
     }
-    s->rp_t0 = s->iters_done;
+    s->rp_t0 = (s->hdone / 2);
     s->rp_niters = niters;
     return KMC_OK;
 }
 
-int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
+int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
     if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
-    const long long remaining = s->opts.niter_walker - s->iters_done;
-    if (niters < 0 || niters > remaining) niters = remaining;
+    const long long remaining = 2 * s->opts.niter_walker - s->hdone;
+    if (nhalfsteps < 0 || nhalfsteps > remaining) nhalfsteps = remaining;
     s->last_launches = 0;
     s->timed = false;
-    if (niters <= 0) return KMC_OK;
+    if (nhalfsteps <= 0) return KMC_OK;
     const bool replay = s->opts.mode == KMC_MODE_REPLAY;
-    if (replay && (s->iters_done < s->rp_t0 || s->iters_done + niters > s->rp_t0 + s->rp_niters))
-        return fail(KMC_ERR_STATE, "replay draws cover iterations [%lld, %lld), asked to run [%lld, %lld)",
-                    s->rp_t0, s->rp_t0 + s->rp_niters, s->iters_done, s->iters_done + niters);
+    const long long hbeg = s->hdone, hend = s->hdone + nhalfsteps;
+    if (replay && (hbeg < 2 * s->rp_t0 || hend > 2 * (s->rp_t0 + s->rp_niters)))
+        return fail(KMC_ERR_STATE, "replay draws cover iterations [%lld, %lld), asked to run half-steps [%lld, %lld)",
+                    s->rp_t0, s->rp_t0 + s->rp_niters, hbeg, hend);
     CU_TRY(cudaSetDevice(s->opts.device));
 
     kmc::RunParams p{};
@@ -482,6 +493,9 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     p.rp_t0 = s->rp_t0;
     p.nw = s->nw;
     p.nhalf = (unsigned)s->nhalf;
+    p.shard_begin = (unsigned)s->sbeg;
+    p.shard_end = (unsigned)(s->sbeg + s->scnt);
+    p.chain_nw = s->nl;
     p.nthin = s->opts.nthin;
     p.ns = s->ns;
     const double a = s->opts.a_scale;
@@ -509,7 +523,6 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
         p.bar_base = s->bar_base;
     };
 
-    const long long hbeg = 2 * s->iters_done, hend = 2 * (s->iters_done + niters);
     void *args[] = {&p, s->dn->params.data()};
     p.per_cta = s->per_cta;
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
@@ -517,7 +530,7 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
         const void *kern = s->dn->ops.run[replay ? 1 : 0][0];
         const int blk = s->dn->ops.block >= 256 ? 256 : s->dn->ops.block;
         p.per_cta = (unsigned)blk;  // one walker per thread, one half-step per launch
-        const unsigned grid = (unsigned)((s->nhalf + blk - 1) / blk);
+        const unsigned grid = (unsigned)((s->scnt + blk - 1) / blk);
         for (long long h = hbeg; h < hend; ++h) {
             set_range(h, h + 1);
             CU_TRY(cudaLaunchKernel(kern, dim3(grid), dim3(blk), args, 0, s->stream));
@@ -526,13 +539,28 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     } else {
         const void *kern = s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
         set_range(hbeg, hend);
-        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(s->block), args, s->smem_bytes, s->stream));
+        CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(s->block), args,
+                                           s->use_smem ? s->smem_bytes : 0, s->stream));
         s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid;
         ++s->last_launches;
     }
     CU_TRY(cudaEventRecord(s->ev1, s->stream));
     s->timed = true;
-    s->iters_done += niters;
+    s->hdone = hend;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    if (s->hdone & 1) return fail(KMC_ERR_STATE, "an outer iteration is half done: finish it with kmc_emcee_run_half");
+    return kmc_emcee_run_half(s, niters < 0 ? -1 : 2 * niters);
+}
+
+int32_t kmc_emcee_device_ptrs(kmc_sampler_t s, void **x, void **logp, void **naccept) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    if (x) *x = s->x;
+    if (logp) *logp = s->lp;
+    if (naccept) *naccept = s->nacc;
     return KMC_OK;
 }
 
@@ -578,7 +606,7 @@ int32_t kmc_emcee_progress(kmc_sampler_t s, int64_t *iters_done, double *naccept
     CU_TRY(cudaMemcpyAsync(&houtl, outl, sizeof houtl, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     CU_TRY(cudaGetLastError());
-    if (iters_done) *iters_done = s->iters_done;
+    if (iters_done) *iters_done = (s->hdone / 2);
     if (naccept_mean) *naccept_mean = mean;
     if (naccept_std) *naccept_std = sd;
     if (outliers) *outliers = (int64_t)houtl;
@@ -591,32 +619,38 @@ int32_t kmc_emcee_nsamples(kmc_sampler_t s, int64_t *ns) {
     return KMC_OK;
 }
 
+int32_t kmc_emcee_nlocal(kmc_sampler_t s, int64_t *nl) {
+    if (!s || !nl) return fail(KMC_ERR_INVALID, "NULL argument");
+    *nl = s->nl;
+    return KMC_OK;
+}
+
 int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, double *accept_ratio) {
     if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
     CU_TRY(cudaSetDevice(s->opts.device));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    const long long ns = s->ns, nw = s->nw;
+    const long long ns = s->ns, nl = s->nl;
     const int d = s->d;
     if (ns > 0 && (thetas || logp)) {
         // walkers per staging chunk: <= 64 MiB of [wc][ns][d] doubles
         long long wc = std::max<long long>(32, (64LL << 20) / (sizeof(double) * ns * d));
-        wc = std::min(wc, nw);
+        wc = std::min(wc, nl);
         double *stage = nullptr;
         CU_TRY(dev_alloc(&stage, sizeof(double) * wc * ns * d, s->opts.device));
         cudaError_t e = cudaSuccess;
-        for (long long w0 = 0; w0 < nw && e == cudaSuccess; w0 += wc) {
-            const long long cur = std::min(wc, nw - w0);
+        for (long long w0 = 0; w0 < nl && e == cudaSuccess; w0 += wc) {
+            const long long cur = std::min(wc, nl - w0);
             const dim3 blk(32, 8);
             if (thetas) {
                 const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), (unsigned)d);
-                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_x, stage, ns, nw, w0, cur, d);
+                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_x, stage, ns, nl, w0, cur, d);
                 e = cudaMemcpyAsync(thetas + w0 * ns * d, stage, sizeof(double) * cur * ns * d,
                                     cudaMemcpyDeviceToHost, s->stream);
                 if (e != cudaSuccess) break;
             }
             if (logp) {
                 const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), 1);
-                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_lp, stage, ns, nw, w0, cur, 1);
+                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_lp, stage, ns, nl, w0, cur, 1);
                 e = cudaMemcpyAsync(logp + w0 * ns, stage, sizeof(double) * cur * ns, cudaMemcpyDeviceToHost,
                                     s->stream);
             }
@@ -626,11 +660,13 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
         dev_free(stage);
         if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "copy_results failed: %s", cudaGetErrorString(e));
     }
-    if (accept_ratio) {
-        std::vector<unsigned> h(nw);
-        CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * nw, cudaMemcpyDeviceToHost));
+    if (accept_ratio) {  // this sampler's walkers: its slice of half 0, then of half 1
+        std::vector<unsigned> h(nl);
+        CU_TRY(cudaMemcpy(h.data(), s->nacc + s->sbeg, sizeof(unsigned) * s->scnt, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(h.data() + s->scnt, s->nacc + s->nhalf + s->sbeg, sizeof(unsigned) * s->scnt,
+                          cudaMemcpyDeviceToHost));
         const double den = (double)(s->opts.niter_walker - s->opts.nburnin_walker);  // :291
-        for (long long w = 0; w < nw; ++w) accept_ratio[w] = (double)h[w] / den;
+        for (long long w = 0; w < nl; ++w) accept_ratio[w] = (double)h[w] / den;
     }
     return KMC_OK;
 }

@@ -45,6 +45,8 @@ struct RunParams {
     long long nw;
     unsigned nhalf;
     unsigned per_cta;   // walker positions (of each half) owned by one CTA
+    unsigned shard_begin, shard_end;  // positions of each half this sampler updates (whole half: 0, nhalf)
+    long long chain_nw;               // walkers in the chain store: 2*(shard_end-shard_begin)
     long long h0, h1;   // half-step range, h = 2*t + batch, t = 0-based outer iteration
     long long n0;       // the reference's loop variable n (:245) at t = h0/2
     long long phase0;   // n0 mod nthin (floored)
@@ -146,6 +148,11 @@ struct DrawRec {  // what a walker-step needs from its draws: 4 registers
     double z;
 };
 
+// Row of global walker k (position i of its half) in the chain store: local shard order.
+__device__ __forceinline__ size_t chain_row(const RunParams &p, long long sidx, unsigned batch, unsigned i) {
+    return (size_t)sidx * p.chain_nw + (batch ? (size_t)(p.shard_end - p.shard_begin) : 0) + (i - p.shard_begin);
+}
+
 // Thinned chain store of one walker (:268-272): its current state right after its own update.
 template <int D>
 __device__ __forceinline__ void chain_store(const RunParams &p, size_t o, bool acc, const double (&y)[D],
@@ -162,8 +169,8 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                                                                                     const Dn<D> dn) {
     constexpr int U = in_flight<D>();
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
-    const unsigned base = blockIdx.x * p.per_cta;  // first owned position (in each half)
-    const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
+    const unsigned base = p.shard_begin + blockIdx.x * p.per_cta;  // first owned position (in each half)
+    const unsigned cnt = base >= p.shard_end ? 0u : min(p.per_cta, p.shard_end - base);
 
     DrawRec dr[U];
     auto make_draws = [&](long long h, unsigned l, DrawRec &r) {
@@ -226,7 +233,7 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                     p.lp[k] = p1;
                     p.nacc[k] += 1u;
                 }
-                if (store) chain_store<D>(p, (size_t)sidx * p.nw + k, acc, y, xk[q], p1, lpk[q]);
+                if (store) chain_store<D>(p, chain_row(p, sidx, (unsigned)batch, base + l), acc, y, xk[q], p1, lpk[q]);
             }
         }
         if (batch == 1) {
@@ -294,14 +301,14 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
     const unsigned nthr = blockDim.x;
     const unsigned L = 2 * p.per_cta;
     // ---- the per-thread registers that live across the whole launch -------------------
-    const unsigned wid = blockIdx.x * p.per_cta + threadIdx.x;  // owned position of round 0 (in each half)
+    const unsigned wid = p.shard_begin + blockIdx.x * p.per_cta + threadIdx.x;  // owned position of round 0 (in each half)
     const unsigned sbase = (unsigned)__cvta_generic_to_shared(smem_raw) + 8u * threadIdx.x;  // xs/lps slot of round 0
     const unsigned nbase = (unsigned)__cvta_generic_to_shared(smem_raw) + 8u * (D + 1) * L + 4u * threadIdx.x;
     double *const grow = p.x + (size_t)wid * D;  // own global row of (half 0, round 0)
     unsigned nv;                                 // rounds this thread owns (<= kRounds)
     {
-        const unsigned base = blockIdx.x * p.per_cta;
-        const unsigned cnt = base >= p.nhalf ? 0u : min(p.per_cta, p.nhalf - base);
+        const unsigned base = p.shard_begin + blockIdx.x * p.per_cta;
+        const unsigned cnt = base >= p.shard_end ? 0u : min(p.per_cta, p.shard_end - base);
         nv = cnt > threadIdx.x ? (cnt - threadIdx.x + nthr - 1) / nthr : 0u;
     }
     // slot(half b, round q) = b*per_cta + q*nthr (+ tid, folded into the bases); byte offsets
@@ -378,7 +385,7 @@ __global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunPa
                 sts_f64(sbase + 8u * (D * L + sl), p1);
                 sts_u32(nbase + 4u * sl, lds_u32(nbase + 4u * sl) + 1u);
             }
-            if (store) chain_store<D>(p, (size_t)sidx * p.nw + wid + ro, acc, y, xk, p1, lpk);
+            if (store) chain_store<D>(p, chain_row(p, sidx, batch, wid + q * nthr), acc, y, xk, p1, lpk);
         }
         if (batch == 1) {
             if (n == 0)  // :285-288 burn-in counters are discarded
