@@ -78,26 +78,33 @@ def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=
     begin, count = shard_range(nwalkers, rank, world)
     nhalf = nwalkers // 2
 
+    import contextlib
+    ctx = contextlib.nullcontext()
     if sampler_factory is None:
         _require_plugin(logdensity)
         s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, launch_mode=1,
                     shard=(begin, count))
-        s.set_stream(torch.cuda.current_stream().cuda_stream)   # same stream as the collective's dependencies
+        # kernels and collectives are ordered through ONE explicit torch stream (a NULL handle would
+        # mean "the sampler's own stream" to the library, so the legacy default stream is not used)
+        st = torch.cuda.Stream(device=s.opts.device)
+        s.set_stream(st.cuda_stream)
+        ctx = torch.cuda.stream(st)
         xt = x_tensor(s)
     else:
         s = sampler_factory(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, (begin, count))
         xt = x_view(s)
     try:
-        for h in range(2 * niter_walker):
-            s.run_half(1)
-            half = xt[(h & 1) * nhalf:((h & 1) + 1) * nhalf]          # the half that was just updated
-            mine = half[begin:begin + count]
-            if xt.is_cuda:
-                dist.all_gather_into_tensor(half.view(-1), mine.reshape(-1), group=group)   # in place (NCCL)
-            else:
-                parts = [torch.empty_like(mine) for _ in range(world)]
-                dist.all_gather(parts, mine.clone(), group=group)
-                half.copy_(torch.cat(parts, dim=0))
+        with ctx:
+            for h in range(2 * niter_walker):
+                s.run_half(1)
+                half = xt[(h & 1) * nhalf:((h & 1) + 1) * nhalf]          # the half that was just updated
+                mine = half[begin:begin + count]
+                if xt.is_cuda:
+                    dist.all_gather_into_tensor(half.view(-1), mine.reshape(-1), group=group)   # in place (NCCL)
+                else:
+                    parts = [torch.empty_like(mine) for _ in range(world)]
+                    dist.all_gather(parts, mine.clone(), group=group)
+                    half.copy_(torch.cat(parts, dim=0))
         s.sync()
         lth, llp, lar = s.results()
     finally:
