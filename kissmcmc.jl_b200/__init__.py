@@ -6,7 +6,7 @@ source (julia/).  Import it as `kissmcmc_b200` (the directory name has a dot in 
 repo-root shim kissmcmc_b200.py registers it).
 """
 from ._lib import KmcError, MODE_PHILOX, MODE_REPLAY, SYMBOLS, LIB_PATH, device_count, lib
-from .api import (LogDensity, Sampler, ball_randn, emcee, exponential, gaussian, gaussian_params, lognormal,
+from .api import (LogDensity, Sampler, ball_randn, emcee, exponential, gaussian, gaussian_params, logistic, lognormal,
                   make_theta0s, philox4x32_10, rosenbrock, squash_walkers)
 
 from . import distributed  # noqa: E402  (multi-GPU drivers; imports torch)
@@ -14,6 +14,6 @@ from . import distributed  # noqa: E402  (multi-GPU drivers; imports torch)
 __all__ = [
     "distributed",
     "emcee", "make_theta0s", "squash_walkers", "LogDensity", "Sampler", "exponential", "rosenbrock", "gaussian",
-    "gaussian_params", "lognormal", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "ball_randn",
+    "gaussian_params", "lognormal", "logistic", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "ball_randn",
     "philox4x32_10", "SYMBOLS", "LIB_PATH", "lib",
 ]

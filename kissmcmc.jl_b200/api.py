@@ -102,6 +102,16 @@ def lognormal(mu: float = 0.0, sigma: float = 1.0, device: int = 0) -> LogDensit
     return LogDensity("lognormal", 1, [mu, sigma, math.log(sigma) + 0.5 * math.log(2 * math.pi)], device=device)
 
 
+def logistic(X, y, prior_sigma: float = 10.0, device: int = 0) -> LogDensity:
+    """Bayesian logistic regression (BASELINE.json configs[3]): X [N, d], y [N] in {0, 1}, prior N(0, sigma^2 I).
+    logp(theta) = sum_n (y_n s_n - softplus(s_n)) - |theta|^2 / (2 sigma^2),  s_n = x_n . theta."""
+    X = np.ascontiguousarray(X, dtype=np.float32)
+    y = np.ascontiguousarray(y, dtype=np.float32).ravel()
+    assert X.ndim == 2 and y.size == X.shape[0]
+    data = np.concatenate([X.ravel(), y])
+    return LogDensity("logistic", X.shape[1], [prior_sigma], data=data, device=device)
+
+
 # ------------------------------------------------------------------------------------------
 # Low-level sampler handle
 

@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/kissmcmc_cuda.h"
+#include "kmc_batched.cuh"
 #include "kmc_kernels.cuh"
 
 namespace {
@@ -107,6 +108,7 @@ struct Ops {
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
     int block = 0;               // max threads per CTA of the run kernels
     int min_blocks = 1;          // CTAs per SM the kernels are compiled for
+    int batch = 0;               // 0: fused thread-per-walker kernels; 1: wide Gaussian; 2: logistic (kmc_batched.cuh)
     const void *eval = nullptr;
     size_t dn_bytes = 0;
     int nparams = 0;
@@ -150,7 +152,19 @@ bool ops_for_dim(int d, Ops &o) {
 bool find_ops(int kind, int d, Ops &o) {
     switch (kind) {
         case kmc::KIND_EXPONENTIAL: return ops_for_dim<kmc::Exponential>(d, o);
-        case kmc::KIND_GAUSSIAN: return ops_for_dim<kmc::Gaussian>(d, o);
+        case kmc::KIND_GAUSSIAN:
+            if (ops_for_dim<kmc::Gaussian>(d, o)) return true;
+            if (d > kmc::kWideMaxD) return false;
+            o = Ops();
+            o.batch = 1;  // dense contraction over the active half
+            o.nparams = d + d * d + 1;
+            return true;
+        case kmc::KIND_LOGISTIC:
+            if (d > 64) return false;
+            o = Ops();
+            o.batch = 2;
+            o.nparams = 1;
+            return true;
         case kmc::KIND_ROSENBROCK:
             if (d != 2) return false;
             o = make_ops<kmc::Rosenbrock, 2>();
@@ -181,7 +195,63 @@ struct kmc_density_s {
     int device = 0;
     std::vector<double> params;  // also the by-value kernel argument (padded to >= 1 double)
     Ops ops;
+    double *d_params = nullptr;  // batched plugins: parameters in device memory
+    float *d_X = nullptr, *d_y = nullptr;  // logistic: data
+    long long ndata = 0;
 };
+
+namespace {
+
+// Batched log-density of npts device-resident points (K4 for the batched plugins; stage 2 of
+// the batched half-step).  `scratch` holds the logistic partial sums ([chunks][npts]).
+struct BatchScratch {
+    double *part = nullptr;
+    size_t bytes = 0;
+};
+
+constexpr int kLogitChunks = 64;
+
+cudaError_t batch_scratch_reserve(BatchScratch &sc, const kmc_density_s &dn, long long npts) {
+    if (dn.ops.batch != 2) return cudaSuccess;
+    const size_t need = sizeof(double) * kLogitChunks * (size_t)npts;
+    if (need <= sc.bytes) return cudaSuccess;
+    dev_free(sc.part);
+    sc.part = nullptr;
+    sc.bytes = 0;
+    cudaError_t e = dev_alloc(&sc.part, need, dn.device);
+    if (e == cudaSuccess) sc.bytes = need;
+    return e;
+}
+
+cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long long npts, double *out,
+                              BatchScratch &sc, cudaStream_t st) {
+    const int d = dn.d;
+    if (dn.ops.batch == 1) {
+        const int dp = d | 1;
+        const size_t smem = sizeof(double) * ((size_t)d * dp + 8 * (size_t)d);
+        cudaError_t e = cudaFuncSetAttribute(kmc::gaussian_wide_logp_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)std::min<long long>((npts + 7) / 8, 2 * 148);
+        kmc::gaussian_wide_logp_kernel<<<grid, 256, smem, st>>>(X, out, npts, d, dn.d_params);
+        return cudaGetLastError();
+    }
+    if (dn.ops.batch == 2) {
+        cudaError_t e = batch_scratch_reserve(sc, dn, npts);
+        if (e != cudaSuccess) return e;
+        const long long rows = (dn.ndata + kLogitChunks - 1) / kLogitChunks;
+        const size_t smem = sizeof(double) * ((size_t)kmc::kLogitTile * d + 8 * kmc::kLogitTile);
+        const dim3 grid((unsigned)((npts + kmc::kLogitTile - 1) / kmc::kLogitTile), kLogitChunks);
+        kmc::logistic_logp_kernel<<<grid, 256, smem, st>>>(X, sc.part, npts, d, dn.d_X, dn.d_y, dn.ndata, rows);
+        const double sg = dn.params[0];
+        kmc::logistic_finish_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(X, sc.part, out, npts, d,
+                                                                                     kLogitChunks, 0.5 / (sg * sg));
+        return cudaGetLastError();
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace
 
 struct kmc_sampler_s {
     kmc_density_s *dn = nullptr;
@@ -207,6 +277,8 @@ struct kmc_sampler_s {
     size_t smem_bytes = 0;
     bool use_smem = false;           // owned state is shared-memory resident (emcee_smem_kernel)
     unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
+    kmc::BatchBuf bb{};                     // batched plugins: proposals of the active shard
+    BatchScratch bsc;
 };
 
 extern "C" {
@@ -247,8 +319,6 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
     if (kind < 0) return fail(KMC_ERR_INVALID, "unknown log-density plugin '%s'", name ? name : "(null)");
     if (d < 1) return fail(KMC_ERR_INVALID, "d must be >= 1");
     if (nparams < 0 || (nparams > 0 && !params)) return fail(KMC_ERR_INVALID, "bad params");
-    (void)data;
-    (void)data_bytes;
     Ops ops;
     if (!find_ops(kind, d, ops))
         return fail(KMC_ERR_UNSUPPORTED, "no sm_100a kernel for plugin '%s' with d=%d", name, d);
@@ -260,17 +330,48 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
     h->d = d;
     h->device = device;
     h->ops = ops;
-    h->params.assign(std::max<size_t>(1, ops.dn_bytes / sizeof(double)), 0.0);
+    h->params.assign(std::max<size_t>(std::max<size_t>(1, ops.dn_bytes / sizeof(double)), (size_t)nparams), 0.0);
     if (nparams) memcpy(h->params.data(), params, sizeof(double) * nparams);
     if (kind == kmc::KIND_ROSENBROCK) {  // RN(1/T) for the exact reciprocal-based division (ddiv_by)
         const double T = std::fabs(params[2]);
         h->params[3] = (T > 0x1p-100 && T < 0x1p100) ? 1.0 / params[2] : 0.0;
+    }
+    if (ops.batch) {  // batched plugins keep parameters (and data) in device memory
+        h->params.assign(params, params + nparams);
+        cudaError_t e = cudaSetDevice(device);
+        if (e == cudaSuccess) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ops.batch == 2) {
+            const long long N = data_bytes / (long long)(sizeof(float) * (d + 1));
+            if (!data || N < 1 || N * (long long)(sizeof(float) * (d + 1)) != data_bytes) {
+                kmc_density_destroy(h);
+                return fail(KMC_ERR_INVALID, "logistic needs data = float32 X[N][d] then y[N] (%d+1 floats per row)", d);
+            }
+            if (!(params[0] > 0.0)) {
+                kmc_density_destroy(h);
+                return fail(KMC_ERR_INVALID, "logistic prior_sigma must be > 0");
+            }
+            h->ndata = N;
+            e = dev_alloc(&h->d_X, sizeof(float) * N * d, device);
+            if (e == cudaSuccess) e = dev_alloc(&h->d_y, sizeof(float) * N, device);
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_X, data, sizeof(float) * N * d, cudaMemcpyHostToDevice);
+            if (e == cudaSuccess)
+                e = cudaMemcpy(h->d_y, (const float *)data + N * d, sizeof(float) * N, cudaMemcpyHostToDevice);
+        }
+        if (e != cudaSuccess) {
+            kmc_density_destroy(h);
+            return fail(KMC_ERR_CUDA, "density upload failed: %s", cudaGetErrorString(e));
+        }
     }
     *out = h;
     return KMC_OK;
 }
 
 int32_t kmc_density_destroy(kmc_density_t h) {
+    if (!h) return KMC_OK;
+    dev_free(h->d_params);
+    dev_free(h->d_X);
+    dev_free(h->d_y);
     delete h;
     return KMC_OK;
 }
@@ -283,14 +384,21 @@ int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, doub
     CU_TRY(dev_alloc(&dx, sizeof(double) * nw * h->d, h->device));
     cudaError_t e = dev_alloc(&dl, sizeof(double) * nw, h->device);
     if (e == cudaSuccess) e = cudaMemcpy(dx, thetas, sizeof(double) * nw * h->d, cudaMemcpyHostToDevice);
+    BatchScratch sc;
     if (e == cudaSuccess) {
-        long long nwl = nw;
-        void *args[] = {&dx, &dl, &nwl, h->params.data()};
-        e = cudaLaunchKernel(h->ops.eval, dim3((unsigned)((nw + 255) / 256)), dim3(256), args, 0, nullptr);
+        if (h->ops.batch) {
+            e = launch_batch_logp(*h, dx, nw, dl, sc, nullptr);
+        } else {
+            long long nwl = nw;
+            void *args[] = {&dx, &dl, &nwl, h->params.data()};
+            e = cudaLaunchKernel(h->ops.eval, dim3((unsigned)((nw + 255) / 256)), dim3(256), args, 0, nullptr);
+        }
     }
     if (e == cudaSuccess) e = cudaMemcpy(logp_out, dl, sizeof(double) * nw, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     dev_free(dx);
     dev_free(dl);
+    dev_free(sc.part);
     if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "density eval failed: %s", cudaGetErrorString(e));
     return KMC_OK;
 }
@@ -309,6 +417,11 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     dev_free(s->rp_z);
     dev_free(s->rp_u);
     dev_free(s->scratch);
+    dev_free(s->bb.Y);
+    dev_free(s->bb.z);
+    dev_free(s->bb.u);
+    dev_free(s->bb.p1);
+    dev_free(s->bsc.part);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -380,14 +493,20 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nw, s->stream));
     CU_TRY_S(cudaMemsetAsync(s->barrier, 0, sizeof(unsigned long long), s->stream));
     CU_TRY_S(cudaMemcpyAsync(s->x, theta0s, sizeof(double) * s->nw * d, cudaMemcpyHostToDevice, s->stream));
-    {  // initial log-densities, :209-210
+    if (density->ops.batch) {  // initial log-densities, :209-210, and the proposal buffers of the active shard
+        CU_TRY_S(launch_batch_logp(*density, s->x, s->nw, s->lp, s->bsc, s->stream));
+        CU_TRY_S(dev_alloc(&s->bb.Y, sizeof(double) * s->scnt * d, opts->device));
+        CU_TRY_S(dev_alloc(&s->bb.z, sizeof(double) * s->scnt, opts->device));
+        CU_TRY_S(dev_alloc(&s->bb.u, sizeof(double) * s->scnt, opts->device));
+        CU_TRY_S(dev_alloc(&s->bb.p1, sizeof(double) * s->scnt, opts->device));
+    } else {
         long long nwl = s->nw;
         void *args[] = {&s->x, &s->lp, &nwl, density->params.data()};
         CU_TRY_S(cudaLaunchKernel(density->ops.eval, dim3((unsigned)((s->nw + 255) / 256)), dim3(256), args, 0,
                                   s->stream));
     }
     CU_TRY_S(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, opts->device));
-    {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
+    if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
         auto geometry = [&](const void *kern, int maxblk, int ctas_per_sm, size_t smem_per_walker, bool &fits) {
@@ -526,7 +645,20 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
     void *args[] = {&p, s->dn->params.data()};
     p.per_cta = s->per_cta;
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
-    if (s->opts.launch_mode == 1) {
+    if (s->dn->ops.batch) {  // propose -> batched log-density -> accept, per half-step
+        const unsigned grid = (unsigned)((s->scnt * 32 + 255) / 256);
+        for (long long h = hbeg; h < hend; ++h) {
+            set_range(h, h + 1);
+            const int store = (p.n0 > 0 && p.phase0 == 0) ? 1 : 0;
+            if (replay) kmc::propose_kernel<true><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d);
+            else kmc::propose_kernel<false><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d);
+            CU_TRY(launch_batch_logp(*s->dn, s->bb.Y, s->scnt, s->bb.p1, s->bsc, s->stream));
+            if (replay) kmc::accept_kernel<true><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d, p.n0, store, p.sidx0);
+            else kmc::accept_kernel<false><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d, p.n0, store, p.sidx0);
+            s->last_launches += s->dn->ops.batch == 2 ? 4 : 3;
+        }
+        CU_TRY(cudaGetLastError());
+    } else if (s->opts.launch_mode == 1) {
         const void *kern = s->dn->ops.run[replay ? 1 : 0][0];
         const int blk = s->dn->ops.block >= 256 ? 256 : s->dn->ops.block;
         p.per_cta = (unsigned)blk;  // one walker per thread, one half-step per launch

@@ -1,0 +1,188 @@
+// kmc_batched.cuh -- the half-step as a three-kernel pipeline for log-densities that are
+// dense contractions over the whole active half (d up to 128 Gaussian: [W x d]·[d x d];
+// logistic regression: [W x d]·[d x N] + row reduction):
+//
+//   propose_kernel   draws (src/samplers.jl:250,:252,:260) + proposal y = xj + z(xk - xj) (:255)
+//                    for every active walker of this shard -> Y [W][d], z, u
+//   <density>        logp1[W] = plugin(Y)  (:257)   FP64 CUDA-core kernels here; the tcgen05
+//                    kernels (kmc_tc.cuh) replace exactly this stage
+//   accept_kernel    accept test (:260), state update (:261-265), thinned chain store (:268-272),
+//                    burn-in counter reset (:285-288)
+//
+// The same density kernels serve kmc_density_eval (initial p0s :209, make_theta0s :334-338).
+#pragma once
+#include "kmc_kernels.cuh"
+
+namespace kmc {
+
+struct BatchBuf {
+    double *Y;    // [W][d] proposals of the active walkers of this shard
+    double *z;    // [W]
+    double *u;    // [W]
+    double *p1;   // [W] log-density of the proposals
+};
+
+// One warp per active walker; lanes stride over the components (coalesced row access).
+template <bool REPLAY>
+__global__ void __launch_bounds__(256) propose_kernel(const RunParams p, const BatchBuf b, long long h, int d) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const unsigned W = p.shard_end - p.shard_begin;
+    if (w >= W) return;
+    const unsigned i = p.shard_begin + w;
+    const unsigned batch = (unsigned)(h & 1);
+    unsigned j;
+    double z, u;
+    step_draws<REPLAY>(p, h, i, j, z, u);
+    const double *xk = p.x + ((size_t)(batch ? p.nhalf : 0u) + i) * d;
+    const double *xj = p.x + (size_t)j * d;
+    double *y = b.Y + (size_t)w * d;
+    for (int c = lane; c < d; c += 32) y[c] = dadd(xj[c], dmul(z, dsub(xk[c], xj[c])));  // :255
+    if (lane == 0) {
+        b.z[w] = z;
+        b.u[w] = u;
+    }
+}
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(256) accept_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+                                                     long long n, int store, long long sidx) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const unsigned W = p.shard_end - p.shard_begin;
+    if (w >= W) return;
+    const unsigned i = p.shard_begin + w;
+    const unsigned batch = (unsigned)(h & 1);
+    const size_t k = (size_t)(batch ? p.nhalf : 0u) + i;
+    const double p1 = b.p1[w], p0 = p.lp[k];
+    const bool acc = accept_exact<false>(p.nm1, b.z[w], p1, p0, b.u[w]);  // :260 (exact FP64; once per walker)
+    double *xk = p.x + k * d;
+    const double *y = b.Y + (size_t)w * d;
+    if (acc)  // :261-265
+        for (int c = lane; c < d; c += 32) xk[c] = y[c];
+    __syncwarp();
+    if (lane == 0) {
+        if (acc) {
+            p.lp[k] = p1;
+            p.nacc[k] += 1u;
+        }
+        if (batch == 1 && n == 0) {  // :285-288 (both halves of this walker position)
+            p.nacc[i] = 0u;
+            p.nacc[(size_t)p.nhalf + i] = 0u;
+        }
+    }
+    if (store) {  // :268-272
+        const size_t o = chain_row(p, sidx, batch, i);
+        for (int c = lane; c < d; c += 32) __stcs(p.chain_x + o * d + c, acc ? y[c] : xk[c]);
+        if (lane == 0) __stcs(p.chain_lp + o, acc ? p1 : p0);
+    }
+}
+
+// ------------------------------------------------------------------ dense Gaussian, FP64
+// params (device): mu[d], A[d][d] row-major, lognorm.  One warp per point; lane l owns rows
+// l, l+32, l+64, l+96 of y = A (x - mu); A is staged transposed in shared memory (At[j][i],
+// conflict-free), the centred point per warp in shared memory (broadcast reads).
+// logp = lognorm - 0.5 * sum_i y_i^2;  FMA accumulation, warp-tree reduction: agrees with the
+// oracle's sequential order to ~1e-14 relative (tolerance stated in the tests: 1e-12).
+constexpr int kWideMaxD = 128;
+
+__global__ void __launch_bounds__(256) gaussian_wide_logp_kernel(const double *__restrict__ X, double *__restrict__ out,
+                                                                 long long npts, int d, const double *__restrict__ prm) {
+    extern __shared__ double sm[];
+    const int dp = d | 1;  // odd row pitch: conflict-free transposed reads
+    double *At = sm;                     // [d][dp]  At[j*dp + i] = A[i][j]
+    double *cb = sm + (size_t)d * dp;    // [warps][d]
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
+        const int i = e / d, j = e % d;
+        At[j * dp + i] = prm[d + e];
+    }
+    __syncthreads();
+    const double lognorm = prm[d + (size_t)d * d];
+    double *c = cb + (size_t)wib * d;
+    for (long long pt = (long long)blockIdx.x * nwarp + wib; pt < npts; pt += (long long)gridDim.x * nwarp) {
+        const double *x = X + pt * d;
+        for (int j = lane; j < d; j += 32) c[j] = x[j] - prm[j];
+        __syncwarp();
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int j = 0; j < d; ++j) {
+            const double cj = c[j];
+            const double *row = At + j * dp + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+                if (lane + 32 * r < d) acc[r] = fma(row[32 * r], cj, acc[r]);
+        }
+        double ss = 0.0;
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+            if (lane + 32 * r < d) ss = fma(acc[r], acc[r], ss);
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) out[pt] = lognorm - 0.5 * ss;
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------ logistic regression, FP64
+// data: X[N][d] float32 row-major then y[N] float32 (0/1); params: [prior_sigma].
+//   logp(theta) = sum_n (y_n s_n - softplus(s_n)) - 0.5 |theta|^2 / sigma^2,  s_n = x_n . theta
+// Exact FP64 reference path: grid (point tiles of 32) x (data chunks); a CTA keeps 32 points'
+// theta in shared memory, each thread streams data rows and accumulates the 32 partial sums
+// in registers; CTA tree reduction into part[chunk][point], finished in fixed chunk order
+// (bit-reproducible).  Summation order differs from the oracle's sequential sum: tolerance
+// 1e-10 relative on logp (stated in the tests).
+constexpr int kLogitTile = 32;
+
+__device__ __forceinline__ double softplus64(double s) { return fmax(s, 0.0) + log1p(exp(-fabs(s))); }
+
+// part[chunk][pt] partial sums, then a fixed-order finish: bit-reproducible run to run.
+__global__ void __launch_bounds__(256) logistic_logp_kernel(const double *__restrict__ TH, double *__restrict__ part,
+                                                            long long npts, int d, const float *__restrict__ X,
+                                                            const float *__restrict__ yv, long long N,
+                                                            long long rows_per_chunk) {
+    extern __shared__ double sm[];
+    double *th = sm;                                  // [kLogitTile][d]
+    double *red = sm + (size_t)kLogitTile * d;        // [warps][kLogitTile]
+    const long long pt0 = (long long)blockIdx.x * kLogitTile;
+    const int npt = (int)min((long long)kLogitTile, npts - pt0);
+    for (int e = threadIdx.x; e < kLogitTile * d; e += blockDim.x)
+        th[e] = (e / d) < npt ? TH[pt0 * d + e] : 0.0;
+    __syncthreads();
+    double acc[kLogitTile];
+#pragma unroll
+    for (int w = 0; w < kLogitTile; ++w) acc[w] = 0.0;
+    const long long n0 = (long long)blockIdx.y * rows_per_chunk, n1 = min(N, n0 + rows_per_chunk);
+    for (long long n = n0 + threadIdx.x; n < n1; n += blockDim.x) {
+        const float *xr = X + n * d;
+        const double yn = (double)yv[n];
+#pragma unroll
+        for (int w = 0; w < kLogitTile; ++w) {
+            double s = 0.0;
+            for (int c = 0; c < d; ++c) s = fma((double)xr[c], th[w * d + c], s);
+            acc[w] += yn * s - softplus64(s);
+        }
+    }
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int w = 0; w < kLogitTile; ++w) {
+        double v = acc[w];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) red[wib * kLogitTile + w] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < npt) {
+        double v = 0.0;
+        for (int k = 0; k < nwarp; ++k) v += red[k * kLogitTile + threadIdx.x];
+        part[(size_t)blockIdx.y * npts + pt0 + threadIdx.x] = v;
+    }
+}
+
+__global__ void logistic_finish_kernel(const double *__restrict__ TH, const double *__restrict__ part,
+                                       double *__restrict__ out, long long npts, int d, int nchunks, double inv2s2) {
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= npts) return;
+    double v = 0.0;
+    for (int k = 0; k < nchunks; ++k) v += part[(size_t)k * npts + pt];
+    double nn = 0.0;
+    for (int c = 0; c < d; ++c) nn = fma(TH[pt * d + c], TH[pt * d + c], nn);
+    out[pt] = v - nn * inv2s2;
+}
+
+}  // namespace kmc

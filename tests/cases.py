@@ -41,3 +41,14 @@ def ball(theta0, radius, nw, seed):
     th0 = np.atleast_1d(np.asarray(theta0, dtype=np.float64))
     x = th0[None, :] + radius * rng.standard_normal((nw, th0.size))
     return x
+
+
+def logistic_problem(N=20000, d=32, seed=0):
+    """Synthetic Bayesian logistic regression (BASELINE.json configs[3], scaled): X ~ N(0,1) rounded to
+    bf16-representable values, theta* ~ N(0,1)/sqrt(d), y ~ Bernoulli(sigmoid(X theta*))."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, d)).astype(np.float32)
+    X = (X.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)        # exact in bf16
+    tstar = rng.standard_normal(d) / np.sqrt(d)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X.astype(np.float64) @ tstar)))).astype(np.float32)
+    return X, y, tstar

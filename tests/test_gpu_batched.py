@@ -1,0 +1,110 @@
+"""GPU parity tests (`-m gpu`) of the batched plugins -- dense Gaussian with d up to 128 (BASELINE.json
+configs[2]) and Bayesian logistic regression (configs[3]) -- through the C-ABI against the CPU oracle.
+
+These log-densities are long dot products: the CUDA kernels accumulate with FMA in a different
+(parallel) order than the oracle's sequential loop, so log-densities agree to a stated relative
+tolerance (1e-12 Gaussian, 1e-10 logistic) instead of bit-for-bit.  Decisions are compared in
+REPLAY mode, where both sides see the same draws: the oracle's smallest decision margin
+|lhs - log u| is asserted to be far above the log-density tolerance, so every accept/reject must
+agree exactly; states x are produced by exact IEEE sub/mul/add and are compared bit-for-bit."""
+import numpy as np
+import pytest
+
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _gauss(km, orc, d, seed=3):
+    prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, seed))
+    return km.LogDensity("gaussian", d, prm), orc.Density("gaussian", d, prm)
+
+
+@pytest.mark.parametrize("d", [17, 32, 100, 128])
+def test_wide_gaussian_eval(km, orc, d):
+    ld, od = _gauss(km, orc, d)
+    pts = np.random.default_rng(0).standard_normal((777, d)) * 2
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-12, atol=0)
+
+
+def test_wide_gaussian_d129_unsupported(km):
+    with pytest.raises(km.KmcError) as e:
+        km.LogDensity("gaussian", 129, np.zeros(129 + 129 * 129 + 1))
+    assert e.value.code == 3
+
+
+@pytest.mark.parametrize("d,nw,nitw,nbw,nthin", [(100, 512, 12, 4, 2), (40, 200, 9, 0, 1)])
+def test_wide_gaussian_replay_parity(km, orc, d, nw, nitw, nbw, nthin):
+    ld, od = _gauss(km, orc, d)
+    x0 = cases.ball(np.zeros(d), 0.5, nw, 5)
+    want = orc.emcee(od, x0, nitw, nbw, nthin, 2.0, seed=21, trace=True, nthreads=4)
+    assert want["min_margin"] > 1e-8            # no decision within reach of a 1e-12 relative log-density error
+    for replay in (want["trace"][:3], None):    # replay of the oracle's draws, then the device's own Philox stream
+        s = km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, 21, km.MODE_REPLAY if replay is not None else km.MODE_PHILOX)
+        if replay is not None:
+            s.set_replay(*replay)
+        s.run(-1)
+        th, lp, ar = s.results()
+        x, l, na = s.state()
+        s.close()
+        assert np.array_equal(ar, want["accept_ratio"]) and np.array_equal(na, want["naccept"])   # decisions exact
+        assert np.array_equal(th, want["chain_x"]) and np.array_equal(x, want["x"])               # states bit-exact
+        np.testing.assert_allclose(lp, want["chain_lp"], rtol=1e-12)
+        np.testing.assert_allclose(l, want["lp"], rtol=1e-12)
+
+
+def test_wide_gaussian_statistics(km):
+    """Free-running: posterior mean / marginal std of a 100-D correlated Gaussian within Monte Carlo error."""
+    d, nw = 100, 2048
+    mean, cov = np.linspace(-1, 1, d), cases.spd_cov(d, 3)
+    ld = km.gaussian(mean, cov)
+    x0 = mean + cases.ball(np.zeros(d), 1.0, nw, 1)
+    th, ar, lp, _ = km.emcee(ld, x0, niter=600 * nw, nburnin=400 * nw, nthin=20, use_progress_meter=False, seed=2)
+    t, a, _, _ = km.squash_walkers(th, ar)
+    sd = np.sqrt(np.diag(cov))
+    assert a > 0.1
+    assert np.all(np.abs(t.mean(0) - mean) < 0.25 * sd)
+    assert np.all(np.abs(t.std(0) - sd) < 0.25 * sd)
+
+
+def test_logistic_eval_and_validation(km, orc):
+    X, y, tstar = cases.logistic_problem(N=5000, d=32, seed=1)
+    ld = km.logistic(X, y, prior_sigma=10.0)
+    od = orc.Density("logistic", 32, [10.0], data=np.concatenate([X.ravel(), y]))
+    pts = tstar + 0.05 * np.random.default_rng(2).standard_normal((70, 32))
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-10)
+    with pytest.raises(km.KmcError):
+        km.LogDensity("logistic", 32, [10.0])                       # no data
+    with pytest.raises(km.KmcError):
+        km.LogDensity("logistic", 32, [-1.0], data=np.concatenate([X.ravel(), y]))
+
+
+def test_logistic_replay_parity(km, orc):
+    d, N, nw, nitw, nbw, nthin = 8, 3000, 64, 10, 4, 3
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=4)
+    ld = km.logistic(X, y, prior_sigma=10.0)
+    od = orc.Density("logistic", d, [10.0], data=np.concatenate([X.ravel(), y]))
+    x0 = tstar + cases.ball(np.zeros(d), 0.02, nw, 7)
+    want = orc.emcee(od, x0, nitw, nbw, nthin, 2.0, seed=9, trace=True, nthreads=4)
+    assert want["min_margin"] > 1e-6
+    s = km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, 9, km.MODE_REPLAY)
+    s.set_replay(*want["trace"][:3])
+    s.run(-1)
+    th, lp, ar = s.results()
+    s.close()
+    assert np.array_equal(ar, want["accept_ratio"]) and np.array_equal(th, want["chain_x"])
+    np.testing.assert_allclose(lp, want["chain_lp"], rtol=1e-10)
+
+
+def test_logistic_posterior_recovers_truth(km):
+    """Free-running on N=20000, d=8: posterior mean within 4 posterior std of theta*, std ~ 1/sqrt(N) scale."""
+    d, N, nw = 8, 20000, 256
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=5)
+    ld = km.logistic(X, y, prior_sigma=10.0)
+    x0 = tstar + cases.ball(np.zeros(d), 0.01, nw, 3)
+    th, ar, lp, _ = km.emcee(ld, x0, niter=300 * nw, nburnin=150 * nw, nthin=5, use_progress_meter=False, seed=6)
+    t, a, _, _ = km.squash_walkers(th, ar)
+    assert a > 0.1
+    sd = t.std(0)
+    assert np.all(sd < 0.05) and np.all(sd > 0.005)
+    assert np.all(np.abs(t.mean(0) - tstar) < 5 * sd + 0.02)
