@@ -47,6 +47,10 @@ WORKLOADS = {
                          desc="BASELINE.json configs[1]: 2-D Rosenbrock/20, 2^20 walkers, 10^4 iterations per walker"),
     "gaussian10d": dict(plugin="gaussian", d=10, nw=1 << 24, niter_walker=200, nthin=100,
                         desc="BASELINE.json configs[4] ensemble: 10-D Gaussian, 2^24 walkers (per GPU), 200 iterations"),
+    "gaussian100d": dict(plugin="gaussian", d=100, nw=1 << 16, niter_walker=400, nthin=100,
+                         desc="BASELINE.json configs[2]: 100-D dense correlated Gaussian, 2^16 walkers, 400 iterations"),
+    "logistic32d": dict(plugin="logistic", d=32, nw=8192, niter_walker=4, nthin=1, ndata=1_000_000,
+                        desc="BASELINE.json configs[3]: Bayesian logistic regression d=32, N=10^6, 8192 walkers, 4 iterations"),
     "exponential1d": dict(plugin="exponential", d=1, nw=100, niter_walker=1000, nthin=1,
                           desc="BASELINE.json configs[0]: README exponential, 100 walkers, niter=10^5"),
 }
@@ -67,6 +71,12 @@ def make_inputs(wl, seed):
         from tests import cases
         params = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 1))
         x0 = 0.1 * rng.standard_normal((nw, d))
+    elif wl["plugin"] == "logistic":
+        from tests import cases
+        X, y, tstar = cases.logistic_problem(N=wl["ndata"], d=d, seed=seed)
+        wl["_data"] = np.concatenate([X.ravel(), y])
+        params = [10.0]
+        x0 = tstar + 1e-3 * rng.standard_normal((nw, d))
     else:
         params = []
         x0 = np.abs(0.5 + 0.1 * rng.standard_normal((nw, d)))
@@ -130,7 +140,7 @@ def run_reference(args, wl):
     from oracle import oracle
     nthreads = os.cpu_count() or 1
     params, x0 = make_inputs(wl, 1)
-    dens = oracle.Density(wl["plugin"], wl["d"], params)
+    dens = oracle.Density(wl["plugin"], wl["d"], params, data=wl.get("_data"))
     nw = wl["nw"]
     # calibrate so one step is ~4 s of CPU work (the whole run stays within a few minutes)
     t0 = time.perf_counter()
@@ -166,7 +176,7 @@ def cpu_baseline(wl, seconds=12.0):
     from oracle import oracle
     nthreads = os.cpu_count() or 1
     params, x0 = make_inputs(wl, 1)
-    dens = oracle.Density(wl["plugin"], wl["d"], params)
+    dens = oracle.Density(wl["plugin"], wl["d"], params, data=wl.get("_data"))
     t0 = time.perf_counter()
     oracle.emcee(dens, x0, 2, 1, 1, 2.0, seed=1, store=False, nthreads=nthreads, native=True)
     per_iter = max((time.perf_counter() - t0) / 2, 1e-6)
@@ -217,7 +227,7 @@ def main():
     nbw = nitw // 2
     ns = (nitw - nbw) // nthin
     params, x0 = make_inputs(wl, 1000 + rank)
-    ld = km.LogDensity(wl["plugin"], d, params, device=local)
+    ld = km.LogDensity(wl["plugin"], d, params, data=wl.get("_data"), device=local)
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 

@@ -85,6 +85,11 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                            const void *data, int64_t data_bytes, int32_t device,
                            kmc_density_t *out);
 int32_t kmc_density_destroy(kmc_density_t h);
+/* Options: "tensor_cores" = 0/1 (logistic with d = 32 and bf16-representable data runs its
+ * walkers x data logits GEMM on tcgen05 tensor cores by default; 0 forces the FP64 kernel).
+ * Info keys: "tensor_cores" (1 if the tcgen05 path will be used), "batched". */
+int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value);
+int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value);
 /* Batched log-density of nw points (host in, host out).  Used for the initial p0s
  * (src/samplers.jl:209-210) and by make_theta0s (:334-338). */
 int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, double *logp_out);

@@ -16,7 +16,8 @@ MODE_PHILOX, MODE_REPLAY = 0, 1
 # every symbol include/kissmcmc_cuda.h declares
 SYMBOLS = [
     "kmc_version", "kmc_last_error", "kmc_device_count", "kmc_trim",
-    "kmc_density_create", "kmc_density_destroy", "kmc_density_eval",
+    "kmc_density_create", "kmc_density_destroy", "kmc_density_eval", "kmc_density_set_option",
+    "kmc_density_get_info",
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
     "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
     "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state",
@@ -53,6 +54,8 @@ lib.kmc_device_count.argtypes = [C.POINTER(C.c_int32)]
 lib.kmc_density_create.argtypes = [C.c_char_p, C.c_int32, _dp, C.c_int64, C.c_void_p, C.c_int64,
                                    C.c_int32, C.POINTER(C.c_void_p)]
 lib.kmc_density_destroy.argtypes = [C.c_void_p]
+lib.kmc_density_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_double]
+lib.kmc_density_get_info.argtypes = [C.c_void_p, C.c_char_p, _dp]
 lib.kmc_density_eval.argtypes = [C.c_void_p, _dp, C.c_int64, _dp]
 lib.kmc_emcee_create.argtypes = [C.c_void_p, _dp, C.c_int64, C.c_int32, C.POINTER(EmceeOpts),
                                  C.POINTER(C.c_void_p)]

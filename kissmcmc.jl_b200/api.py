@@ -62,6 +62,14 @@ class LogDensity:
         out = self.eval(th.reshape(-1, self.d))
         return float(out[0]) if single else out
 
+    def set_option(self, key: str, value: float):
+        check(lib.kmc_density_set_option(self._h, key.encode(), float(value)))
+
+    def info(self, key: str) -> float:
+        v = C.c_double()
+        check(lib.kmc_density_get_info(self._h, key.encode(), C.byref(v)))
+        return v.value
+
     def eval(self, thetas) -> np.ndarray:
         th = np.ascontiguousarray(np.asarray(thetas, dtype=np.float64).reshape(-1, self.d))
         out = np.empty(th.shape[0])

@@ -15,6 +15,7 @@
 
 #include "../../include/kissmcmc_cuda.h"
 #include "kmc_batched.cuh"
+#include "kmc_tc.cuh"
 #include "kmc_kernels.cuh"
 
 namespace {
@@ -198,6 +199,12 @@ struct kmc_density_s {
     double *d_params = nullptr;  // batched plugins: parameters in device memory
     float *d_X = nullptr, *d_y = nullptr;  // logistic: data
     long long ndata = 0;
+    // logistic on tcgen05 (kmc_tc.cuh): bf16 copy of X, X^T y, TMA map of X
+    bool tc_ok = false, tc_on = true;
+    __nv_bfloat16 *d_Xbf = nullptr;
+    double *d_xty = nullptr;
+    CUtensorMap mapX;
+    int nsm = 148;
 };
 
 namespace {
@@ -207,13 +214,77 @@ namespace {
 struct BatchScratch {
     double *part = nullptr;
     size_t bytes = 0;
+    __nv_bfloat16 *pieces = nullptr;  // tcgen05 path: theta split into 3 bf16 pieces [3][wpad][d]
+    size_t pieces_bytes = 0;
 };
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(ptr);
+    }
+    return fn;
+}
+
+// 2-D bf16 row-major [rows][32] tensor, box = [box_rows][32], 64-byte swizzle (K-major UMMA operand)
+bool make_map_bf16_k32(CUtensorMap *map, const void *base, unsigned long long rows, unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {32, rows};
+    const cuuint64_t strides[1] = {64};
+    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 constexpr int kLogitChunks = 64;
 
+struct TcPlan {
+    kmc::tc::LogitParams lp;
+    unsigned grid;
+};
+
+TcPlan tc_plan(const kmc_density_s &dn, long long npts) {
+    TcPlan pl{};
+    pl.lp.W = npts;
+    pl.lp.N = dn.ndata;
+    pl.lp.mtiles = (int)((npts + kmc::tc::BM - 1) / kmc::tc::BM);
+    pl.lp.ntiles = (int)((dn.ndata + kmc::tc::BN - 1) / kmc::tc::BN);
+    int nch = (dn.nsm * 8 + pl.lp.mtiles - 1) / pl.lp.mtiles;
+    nch = std::max(1, std::min(nch, std::min(pl.lp.ntiles, 512)));
+    pl.lp.tiles_per_chunk = (pl.lp.ntiles + nch - 1) / nch;
+    pl.lp.nchunks = (pl.lp.ntiles + pl.lp.tiles_per_chunk - 1) / pl.lp.tiles_per_chunk;
+    pl.lp.wpad = (long long)pl.lp.mtiles * kmc::tc::BM;
+    pl.grid = (unsigned)std::min<long long>((long long)pl.lp.mtiles * pl.lp.nchunks, dn.nsm);
+    return pl;
+}
+
 cudaError_t batch_scratch_reserve(BatchScratch &sc, const kmc_density_s &dn, long long npts) {
     if (dn.ops.batch != 2) return cudaSuccess;
-    const size_t need = sizeof(double) * kLogitChunks * (size_t)npts;
+    const bool tcp = dn.tc_ok && dn.tc_on;
+    const TcPlan pl = tcp ? tc_plan(dn, npts) : TcPlan{};
+    if (tcp) {
+        const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)pl.lp.wpad * dn.d;
+        if (pneed > sc.pieces_bytes) {
+            dev_free(sc.pieces);
+            sc.pieces = nullptr;
+            sc.pieces_bytes = 0;
+            cudaError_t e = dev_alloc(&sc.pieces, pneed, dn.device);
+            if (e != cudaSuccess) return e;
+            sc.pieces_bytes = pneed;
+        }
+    }
+    const size_t need = sizeof(double) * (size_t)(tcp ? pl.lp.nchunks : kLogitChunks) * (size_t)npts;
     if (need <= sc.bytes) return cudaSuccess;
     dev_free(sc.part);
     sc.part = nullptr;
@@ -234,6 +305,25 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         if (e != cudaSuccess) return e;
         const unsigned grid = (unsigned)std::min<long long>((npts + 7) / 8, 2 * 148);
         kmc::gaussian_wide_logp_kernel<<<grid, 256, smem, st>>>(X, out, npts, d, dn.d_params);
+        return cudaGetLastError();
+    }
+    if (dn.ops.batch == 2 && dn.tc_ok && dn.tc_on) {  // tcgen05 logits GEMM + fused softplus row sums
+        cudaError_t e = batch_scratch_reserve(sc, dn, npts);
+        if (e != cudaSuccess) return e;
+        TcPlan pl = tc_plan(dn, npts);
+        pl.lp.part = sc.part;
+        const long long ne = pl.lp.wpad * d;
+        kmc::tc::split_theta_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, sc.pieces, npts, pl.lp.wpad, d);
+        CUtensorMap mapA;
+        if (!make_map_bf16_k32(&mapA, sc.pieces, (unsigned long long)kmc::tc::PIECES * pl.lp.wpad, kmc::tc::BM))
+            return cudaErrorInvalidValue;
+        const size_t smem = sizeof(kmc::tc::Smem) + 1024;
+        e = cudaFuncSetAttribute(kmc::tc::logistic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kmc::tc::logistic_tc_kernel<<<pl.grid, kmc::tc::kThreads, smem, st>>>(mapA, dn.mapX, pl.lp);
+        const double sg = dn.params[0];
+        kmc::tc::logistic_tc_finish_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(
+            X, sc.part, dn.d_xty, out, npts, d, pl.lp.nchunks, 0.5 / (sg * sg));
         return cudaGetLastError();
     }
     if (dn.ops.batch == 2) {
@@ -357,6 +447,31 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
             if (e == cudaSuccess) e = cudaMemcpy(h->d_X, data, sizeof(float) * N * d, cudaMemcpyHostToDevice);
             if (e == cudaSuccess)
                 e = cudaMemcpy(h->d_y, (const float *)data + N * d, sizeof(float) * N, cudaMemcpyHostToDevice);
+            // tcgen05 path: d == 32 and every X value exactly representable in bf16
+            if (e == cudaSuccess && d == kmc::tc::BK) {
+                const uint32_t *xb = reinterpret_cast<const uint32_t *>(data);
+                bool exact = true;
+                for (long long i = 0; i < N * d && exact; ++i) exact = (xb[i] & 0xFFFFu) == 0;
+                int nsm = 0;
+                cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+                h->nsm = nsm > 0 ? nsm : 148;
+                if (exact) {
+                    std::vector<double> xty(d, 0.0);  // X^T y in FP64: the y_n s_n term is then an exact d-dot
+                    const float *Xh = (const float *)data, *yh = Xh + N * d;
+                    for (long long n = 0; n < N; ++n)
+                        if (yh[n] != 0.0f)
+                            for (int c = 0; c < d; ++c) xty[c] += (double)yh[n] * (double)Xh[n * d + c];
+                    e = dev_alloc(&h->d_Xbf, sizeof(__nv_bfloat16) * N * d, device);
+                    if (e == cudaSuccess) e = dev_alloc(&h->d_xty, sizeof(double) * d, device);
+                    if (e == cudaSuccess) e = cudaMemcpy(h->d_xty, xty.data(), sizeof(double) * d, cudaMemcpyHostToDevice);
+                    if (e == cudaSuccess) {
+                        kmc::tc::f32_to_bf16_kernel<<<(unsigned)((N * d + 255) / 256), 256>>>(h->d_X, h->d_Xbf, N * d);
+                        e = cudaDeviceSynchronize();
+                    }
+                    if (e == cudaSuccess)
+                        h->tc_ok = make_map_bf16_k32(&h->mapX, h->d_Xbf, (unsigned long long)N, kmc::tc::BN);
+                }
+            }
         }
         if (e != cudaSuccess) {
             kmc_density_destroy(h);
@@ -367,11 +482,35 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
     return KMC_OK;
 }
 
+int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value) {
+    if (!h || !key) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "tensor_cores")) {
+        h->tc_on = value != 0.0;
+        return KMC_OK;
+    }
+    return fail(KMC_ERR_INVALID, "unknown option '%s'", key);
+}
+
+int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value) {
+    if (!h || !key || !value) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (!strcmp(key, "tensor_cores")) {
+        *value = (h->tc_ok && h->tc_on) ? 1.0 : 0.0;
+        return KMC_OK;
+    }
+    if (!strcmp(key, "batched")) {
+        *value = h->ops.batch;
+        return KMC_OK;
+    }
+    return fail(KMC_ERR_INVALID, "unknown info key '%s'", key);
+}
+
 int32_t kmc_density_destroy(kmc_density_t h) {
     if (!h) return KMC_OK;
     dev_free(h->d_params);
     dev_free(h->d_X);
     dev_free(h->d_y);
+    dev_free(h->d_Xbf);
+    dev_free(h->d_xty);
     delete h;
     return KMC_OK;
 }
@@ -399,6 +538,7 @@ int32_t kmc_density_eval(kmc_density_t h, const double *thetas, int64_t nw, doub
     dev_free(dx);
     dev_free(dl);
     dev_free(sc.part);
+    dev_free(sc.pieces);
     if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "density eval failed: %s", cudaGetErrorString(e));
     return KMC_OK;
 }
@@ -422,6 +562,7 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     dev_free(s->bb.u);
     dev_free(s->bb.p1);
     dev_free(s->bsc.part);
+    dev_free(s->bsc.pieces);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);

@@ -1,0 +1,334 @@
+// kmc_tc.cuh -- tcgen05 (5th-gen tensor core) log-density kernels for sm_100a.
+//
+// K3  logistic_tc_kernel: the walkers x data logits GEMM of Bayesian logistic regression
+//     (BASELINE.json configs[3]) fused with its softplus row reduction.
+//
+//       S[w][n] = theta_w . x_n          [W x 32] . [32 x N]   (N ~ 1e6 streamed, W = active half)
+//       out[w]  = sum_n softplus(S[w][n])
+//
+//     The caller adds the exact FP64 terms  theta.(X^T y)  and the prior (logistic_tc_finish_kernel).
+//
+//   * operands: X is bf16 (the plugin requires bf16-representable data, checked at creation, so
+//     this is exact); theta (FP64) is split into three bf16 pieces hi+mid+lo (24 significant
+//     bits).  bf16 x bf16 products are exact in FP32, the accumulation is FP32 in TMEM:
+//     logits carry ~1e-6 absolute error, the row sum over 1e6 data points ~3e-4 (stated
+//     tolerance on the log-density DIFFERENCE in the tests: 2e-3 at N = 1e6).
+//   * one CTA per SM, persistent over work items (walker tile of 128, chunk of data tiles):
+//       warp 0     TMA producer: A = 3 theta pieces [128 x 32] once per item, B = X tile
+//                  [256 x 32] per stage (4 stages), SWIZZLE_64B K-major, mbarrier complete_tx
+//       warp 1     MMA issuer: one elected thread, 6 x tcgen05.mma.cta_group::1.kind::f16
+//                  (M=128, N=256, K=16) per tile = 3 pieces x 2 k-steps, lo piece first;
+//                  tcgen05.commit frees the smem stage and publishes the accumulator
+//       warps 2-9  epilogue: tcgen05.ld 32x32b.x32 from the double-buffered TMEM accumulator
+//                  (2 x 256 columns = all 512), softplus in FP32 on MUFU ex2/lg2, FP32 partial
+//                  per 32 columns, FP64 running sum per row, tail columns masked
+//   * every mbarrier wait has a watchdog (trap after ~2 s) so a bad descriptor cannot hang the GPU.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace kmc {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4, ACC = 2, PIECES = 3;
+constexpr int kEpiWarps = 8;
+constexpr int kThreads = 32 * (2 + kEpiWarps);
+constexpr int kABytes = BM * BK * 2;  // 8 KB per theta piece
+constexpr int kBBytes = BN * BK * 2;  // 16 KB per X tile
+
+struct __align__(1024) Smem {
+    unsigned char a[PIECES][kABytes];
+    unsigned char b[STAGES][kBBytes];
+    unsigned long long full[STAGES], empty[STAGES], tfull[ACC], tempty[ACC], afull, aempty;
+    unsigned tmem_base;
+    double comb[BM];
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = smem_u32(bar);
+    const long long t0 = clock64();
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 4000000000LL) __trap();  // watchdog: never hang the device
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int x, int y, unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(dst)),
+        "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(unsigned long long *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] . B[smem]^T, kind::f16 (bf16 in, fp32 accumulate), issued by one thread
+__device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                       unsigned idesc, unsigned accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// K-major operand tile with 64-byte rows (32 bf16), SWIZZLE_64B: 8-row groups are 512 B apart
+// (SBO), LBO unused (1), descriptor version 1 (sm_100), layout type 4.  cute/arch/mma_sm100_desc.hpp.
+__device__ __forceinline__ unsigned long long smem_desc_sw64(unsigned addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;            // leading byte offset (ignored for swizzled K-major)
+    d |= (unsigned long long)(512 >> 4) << 32;   // stride byte offset: 8 rows x 64 B
+    d |= (unsigned long long)1 << 46;            // version
+    d |= (unsigned long long)4 << 61;            // SWIZZLE_64B
+    return d;
+}
+// kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256.
+__host__ __device__ constexpr unsigned idesc_bf16_f32(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float softplus32(float s) {
+    // max(s,0) + ln2 * lg2(1 + 2^(-|s| log2 e))
+    float t, l;
+    const float a = -fabsf(s) * 1.4426950408889634f;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
+    return fmaf(l, 0.6931471805599453f, fmaxf(s, 0.0f));
+}
+
+struct LogitParams {
+    long long W;          // points (rows of theta)
+    long long N;          // data rows
+    int mtiles;           // ceil(W / 128)
+    int nchunks;          // data chunks (work items per m-tile)
+    int tiles_per_chunk;  // data tiles of 256 rows per chunk
+    int ntiles;           // ceil(N / 256)
+    long long wpad;       // rows per theta piece in the piece buffer (mtiles * 128)
+    double *part;         // [nchunks][W] partial sums of softplus
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
+                   const LogitParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&sm.full[s], 1);
+            mbar_init(&sm.empty[s], 1);
+        }
+        for (int a = 0; a < ACC; ++a) {
+            mbar_init(&sm.tfull[a], 1);
+            mbar_init(&sm.tempty[a], kEpiWarps);
+        }
+        mbar_init(&sm.afull, 1);
+        mbar_init(&sm.aempty, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: all 512 columns (2 accumulators of 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = sm.tmem_base;
+    const int nitems = p.mtiles * p.nchunks;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            unsigned stage = 0, phase = 0, aphase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int mt = item % p.mtiles, ch = item / p.mtiles;
+                mbar_wait(&sm.aempty, aphase ^ 1);  // MMA finished with the previous item's theta tile
+                mbar_expect_tx(&sm.afull, PIECES * kABytes);
+                for (int pc = 0; pc < PIECES; ++pc)
+                    tma_load_2d(sm.a[pc], &mapA, 0, (int)(pc * p.wpad + (long long)mt * BM), &sm.afull);
+                aphase ^= 1;
+                const int t0 = ch * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&sm.empty[stage], phase ^ 1);
+                    mbar_expect_tx(&sm.full[stage], kBBytes);
+                    tma_load_2d(sm.b[stage], &mapX, 0, t * BN, &sm.full[stage]);  // rows past N are zero-filled
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr unsigned idesc = idesc_bf16_f32(BM, BN);
+            unsigned stage = 0, phase = 0, aphase = 0, acc = 0, accphase = 0;
+            for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+                const int ch = item / p.mtiles;
+                mbar_wait(&sm.afull, aphase);
+                aphase ^= 1;
+                tc_fence_after();
+                const int t0 = ch * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    mbar_wait(&sm.tempty[acc], accphase ^ 1);  // epilogue drained this accumulator
+                    mbar_wait(&sm.full[stage], phase);         // X tile landed
+                    tc_fence_after();
+                    const unsigned d = tmem + acc * BN;
+                    const unsigned bbase = smem_u32(sm.b[stage]);
+#pragma unroll
+                    for (int pc = PIECES - 1; pc >= 0; --pc) {  // lo, mid, hi: small terms first
+                        const unsigned abase = smem_u32(sm.a[pc]);
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            tc_mma(d, smem_desc_sw64(abase + k * 32), smem_desc_sw64(bbase + k * 32), idesc,
+                                   (pc != PIECES - 1 || k != 0) ? 1u : 0u);
+                    }
+                    tc_commit(&sm.empty[stage]);  // smem stage reusable once these MMAs retire
+                    tc_commit(&sm.tfull[acc]);    // accumulator ready for the epilogue
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (++acc == ACC) {
+                        acc = 0;
+                        accphase ^= 1;
+                    }
+                }
+                tc_commit(&sm.aempty);  // theta tile reusable once the item's MMAs retire
+            }
+        }
+    } else {
+        // ===================== epilogue: softplus + row sums =====================
+        const int ew = warp - 2;            // 0..7
+        const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*quarter .. +31
+        const int colhalf = ew >> 2;        // columns [0,128) or [128,256) of the accumulator
+        const int row = quarter * 32 + lane;
+        unsigned acc = 0, accphase = 0;
+        for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
+            const int mt = item % p.mtiles, ch = item / p.mtiles;
+            const int t0 = ch * p.tiles_per_chunk, t1 = min(p.ntiles, t0 + p.tiles_per_chunk);
+            double rowsum = 0.0;
+            for (int t = t0; t < t1; ++t) {
+                mbar_wait(&sm.tfull[acc], accphase);
+                tc_fence_after();
+                const long long nvalid = p.N - (long long)t * BN;  // columns of this tile that are real data
+#pragma unroll 1
+                for (int cb = 0; cb < BN / 2; cb += 32) {
+                    const int col0 = colhalf * (BN / 2) + cb;
+                    unsigned v[32];
+                    const unsigned taddr = tmem + ((unsigned)(quarter * 32) << 16) + acc * BN + col0;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                        "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
+                          "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
+                          "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
+                          "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float part = 0.0f;
+                    if (nvalid >= col0 + 32) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) part += softplus32(__uint_as_float(v[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < nvalid) part += softplus32(__uint_as_float(v[j]));
+                    }
+                    rowsum += (double)part;
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+                if (++acc == ACC) {
+                    acc = 0;
+                    accphase ^= 1;
+                }
+            }
+            // combine the two column halves of each row, then one store per (chunk, row)
+            asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+            if (colhalf == 1) sm.comb[row] = rowsum;
+            asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
+            if (colhalf == 0) {
+                const long long w = (long long)mt * BM + row;
+                if (w < p.W) p.part[(size_t)ch * p.W + w] = rowsum + sm.comb[row];
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
+}
+
+// theta (FP64) -> three bf16 pieces hi + mid + lo, rows padded with zeros to wpad.
+__global__ void split_theta_kernel(const double *__restrict__ TH, __nv_bfloat16 *__restrict__ out, long long W,
+                                   long long wpad, int d) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= wpad * d) return;
+    const long long w = e / d;
+    double r = w < W ? TH[e] : 0.0;
+#pragma unroll
+    for (int pc = 0; pc < PIECES; ++pc) {
+        const __nv_bfloat16 h = __double2bfloat16(r);
+        out[(size_t)pc * wpad * d + e] = h;
+        r -= (double)__bfloat162float(h);
+    }
+}
+
+__global__ void f32_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long long n) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) out[e] = __float2bfloat16(in[e]);
+}
+
+// logp = theta . (X^T y) - sum softplus - |theta|^2 / (2 sigma^2); chunks summed in fixed order.
+__global__ void logistic_tc_finish_kernel(const double *__restrict__ TH, const double *__restrict__ part,
+                                          const double *__restrict__ xty, double *__restrict__ out, long long W, int d,
+                                          int nchunks, double inv2s2) {
+    const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    double sp = 0.0;
+    for (int k = 0; k < nchunks; ++k) sp += part[(size_t)k * W + w];
+    double dot = 0.0, nn = 0.0;
+    for (int c = 0; c < d; ++c) {
+        const double t = TH[w * d + c];
+        dot = fma(t, xty[c], dot);
+        nn = fma(t, t, nn);
+    }
+    out[w] = dot - sp - nn * inv2s2;
+}
+
+}  // namespace tc
+}  // namespace kmc

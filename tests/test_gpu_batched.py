@@ -108,3 +108,57 @@ def test_logistic_posterior_recovers_truth(km):
     sd = t.std(0)
     assert np.all(sd < 0.05) and np.all(sd > 0.005)
     assert np.all(np.abs(t.mean(0) - tstar) < 5 * sd + 0.02)
+
+
+# ---------------------------------------------------------------------------------- tcgen05 logistic (K3)
+
+def test_logistic_tensor_core_path_matches_fp64(km):
+    """d = 32 with bf16-representable X runs the logits GEMM on tcgen05 (theta split into 3 bf16 pieces,
+    FP32 accumulation in TMEM, FP32 softplus).  Stated tolerance against the FP64 CUDA-core kernel of the
+    same plugin: |logp_tc - logp_fp64| <= 2e-3 absolute (N = 50k) and the same bound on log-density
+    DIFFERENCES between nearby points, which is what accept decisions see.  N is not a multiple of the
+    256-row tile (tail masking) and W is not a multiple of 128 (padded rows)."""
+    N, d = 50_001, 32
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=11)
+    ld = km.logistic(X, y, prior_sigma=10.0)
+    assert ld.info("tensor_cores") == 1.0 and ld.info("batched") == 2.0
+    pts = tstar + 0.01 * np.random.default_rng(3).standard_normal((300, d))
+    got = ld.eval(pts)
+    ld.set_option("tensor_cores", 0)
+    assert ld.info("tensor_cores") == 0.0
+    want = ld.eval(pts)
+    assert np.all(np.isfinite(got))
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got[1:] - got[:-1], want[1:] - want[:-1], rtol=0, atol=2e-3)
+    # a single point and an exact multiple of the tile sizes
+    ld.set_option("tensor_cores", 1)
+    np.testing.assert_allclose(ld.eval(pts[:1]), want[:1], rtol=0, atol=2e-3)
+    np.testing.assert_allclose(ld.eval(pts[:256]), want[:256], rtol=0, atol=2e-3)
+
+
+def test_logistic_tensor_core_not_used_when_ineligible(km):
+    X, y, _ = cases.logistic_problem(N=2000, d=32, seed=1)
+    X2 = X + np.float32(1e-4)                                   # not bf16-representable any more
+    assert km.logistic(X2, y).info("tensor_cores") == 0.0
+    X8, y8, _ = cases.logistic_problem(N=2000, d=8, seed=1)     # d != 32
+    assert km.logistic(X8, y8).info("tensor_cores") == 0.0
+
+
+def test_logistic_tensor_core_sampling(km):
+    """Same seeded Philox run on the tcgen05 path and on the FP64 path: the log-density noise of the
+    tensor path (<= 2e-3) may flip only decisions that were within that distance of a tie, so almost all
+    accept counts agree and the posterior moments agree within Monte Carlo error."""
+    N, d, nw = 30_000, 32, 512
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=12)
+    ld = km.logistic(X, y, prior_sigma=10.0)
+    x0 = tstar + cases.ball(np.zeros(d), 0.01, nw, 2)
+    kw = dict(niter=120 * nw, nburnin=60 * nw, nthin=4, use_progress_meter=False, seed=3)
+    th_tc, ar_tc, lp_tc, _ = km.emcee(ld, x0, **kw)
+    ld.set_option("tensor_cores", 0)
+    th64, ar64, lp64, _ = km.emcee(ld, x0, **kw)
+    assert ar_tc.mean() > 0.05 and abs(ar_tc.mean() - ar64.mean()) < 0.02
+    t_tc, t64 = th_tc.reshape(-1, d), th64.reshape(-1, d)
+    sd = t64.std(0)
+    assert np.all(np.abs(t_tc.mean(0) - t64.mean(0)) < 0.5 * sd)
+    assert np.all(np.abs(t_tc.std(0) - sd) < 0.3 * sd)
+    assert np.all(np.abs(t_tc.mean(0) - tstar) < 6 * sd + 0.03)
