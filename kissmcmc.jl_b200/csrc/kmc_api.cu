@@ -205,6 +205,9 @@ struct kmc_density_s {
     double *d_xty = nullptr;
     CUtensorMap mapX;
     int nsm = 148;
+    // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
+    __nv_bfloat16 *d_Abf = nullptr;
+    CUtensorMap mapA;
 };
 
 namespace {
@@ -232,6 +235,19 @@ EncodeTiledFn encode_tiled_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(ptr);
     }
     return fn;
+}
+
+// 2-D bf16 row-major [rows][128] tensor, box = [box_rows][64] (128 B), 128-byte swizzle
+bool make_map_bf16_k128(CUtensorMap *map, const void *base, unsigned long long rows, unsigned box_rows) {
+    EncodeTiledFn fn = encode_tiled_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {128, rows};
+    const cuuint64_t strides[1] = {256};
+    const cuuint32_t box[2] = {64, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 // 2-D bf16 row-major [rows][32] tensor, box = [box_rows][32], 64-byte swizzle (K-major UMMA operand)
@@ -297,6 +313,37 @@ cudaError_t batch_scratch_reserve(BatchScratch &sc, const kmc_density_s &dn, lon
 cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long long npts, double *out,
                               BatchScratch &sc, cudaStream_t st) {
     const int d = dn.d;
+    if (dn.ops.batch == 1 && dn.tc_ok && dn.tc_on) {  // tcgen05 Mahalanobis GEMM
+        kmc::tc::GaussParams gp{};
+        gp.W = npts;
+        gp.mtiles = (int)((npts + kmc::tc::BM - 1) / kmc::tc::BM);
+        gp.wpad = (long long)gp.mtiles * kmc::tc::BM;
+        gp.d = d;
+        gp.lognorm = dn.params[d + (size_t)d * d];
+        gp.out = out;
+        const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)gp.wpad * kmc::tc::GK;
+        if (pneed > sc.pieces_bytes) {
+            dev_free(sc.pieces);
+            sc.pieces = nullptr;
+            sc.pieces_bytes = 0;
+            cudaError_t e = dev_alloc(&sc.pieces, pneed, dn.device);
+            if (e != cudaSuccess) return e;
+            sc.pieces_bytes = pneed;
+        }
+        const long long ne = gp.wpad * kmc::tc::GK;
+        kmc::tc::split_rows128_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, dn.d_params, sc.pieces, npts,
+                                                                                    gp.wpad, d);
+        CUtensorMap mapC;
+        if (!make_map_bf16_k128(&mapC, sc.pieces, (unsigned long long)kmc::tc::PIECES * gp.wpad, kmc::tc::BM))
+            return cudaErrorInvalidValue;
+        const size_t smem = sizeof(kmc::tc::GaussSmem) + 1024;
+        cudaError_t e = cudaFuncSetAttribute(kmc::tc::gaussian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)smem);
+        if (e != cudaSuccess) return e;
+        const unsigned grid = (unsigned)std::min<long long>(gp.mtiles, dn.nsm);
+        kmc::tc::gaussian_tc_kernel<<<grid, kmc::tc::kGaussThreads, smem, st>>>(mapC, dn.mapA, gp);
+        return cudaGetLastError();
+    }
     if (dn.ops.batch == 1) {
         const int dp = d | 1;
         const size_t smem = sizeof(double) * ((size_t)d * dp + 8 * (size_t)d);
@@ -431,6 +478,22 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
         if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ops.batch == 1) {  // matrix pieces for the tcgen05 Mahalanobis GEMM
+            int nsm = 0;
+            cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+            h->nsm = nsm > 0 ? nsm : 148;
+            e = dev_alloc(&h->d_Abf, sizeof(__nv_bfloat16) * kmc::tc::PIECES * kmc::tc::GN * kmc::tc::GK, device);
+            if (e == cudaSuccess) {
+                const long long ne = (long long)kmc::tc::GN * kmc::tc::GK;
+                kmc::tc::split_rows128_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(h->d_params + d, nullptr, h->d_Abf, d,
+                                                                                    kmc::tc::GN, d);
+                e = cudaDeviceSynchronize();
+            }
+            if (e == cudaSuccess)
+                h->tc_ok = make_map_bf16_k128(&h->mapA, h->d_Abf, (unsigned long long)kmc::tc::PIECES * kmc::tc::GN,
+                                              kmc::tc::GN);
+            h->tc_on = false;  // exact FP64 kernel by default; opt in with set_option("tensor_cores", 1)
+        }
         if (e == cudaSuccess && ops.batch == 2) {
             const long long N = data_bytes / (long long)(sizeof(float) * (d + 1));
             if (!data || N < 1 || N * (long long)(sizeof(float) * (d + 1)) != data_bytes) {
@@ -511,6 +574,7 @@ int32_t kmc_density_destroy(kmc_density_t h) {
     dev_free(h->d_y);
     dev_free(h->d_Xbf);
     dev_free(h->d_xty);
+    dev_free(h->d_Abf);
     delete h;
     return KMC_OK;
 }

@@ -330,5 +330,190 @@ __global__ void logistic_tc_finish_kernel(const double *__restrict__ TH, const d
     out[w] = dot - sp - nn * inv2s2;
 }
 
+// ======================================================================================
+// K2  gaussian_tc_kernel: batched Mahalanobis form of the dense Gaussian plugin
+//     (BASELINE.json configs[2], d <= 128):   y_w = A (x_w - mu),   out[w] = lognorm - 0.5 |y_w|^2
+//
+//   GEMM  [W x KP] . [KP x NP]^T  with KP = NP = 128 (d zero-padded), M tile = 128 walkers.
+//   Both operands are FP64 on the host side and are split into three bf16 pieces each; the six
+//   piece pairs whose product is above 2^-24 relative are accumulated in FP32 in TMEM, smallest
+//   first:  (lo,hi) (hi,lo) (mid,mid) (mid,hi) (hi,mid) (hi,hi)   [C piece, A piece].
+//   Stated tolerance vs the FP64 kernel: |logp_tc - logp_fp64| <= 1e-5 * (1 + |y|^2).
+//
+//   smem: A pieces 3 x 32 KB resident for the whole kernel + C pieces 3 x 32 KB per walker tile,
+//   each piece = 2 k-halves of [128 rows x 128 B], SWIZZLE_128B K-major (TMA box 64 x 128).
+//   warp 0 TMA, warp 1 MMA (48 x tcgen05.mma M=128 N=128 K=16 per tile), warps 2-5 epilogue
+//   (tcgen05.ld, sum of squares of the first d columns), accumulators double-buffered in TMEM.
+constexpr int GK = 128, GN = 128, GPIECE_BYTES = 2 * BM * 128;  // 32 KB
+constexpr int kGaussThreads = 32 * (2 + 4);
+
+struct __align__(1024) GaussSmem {
+    unsigned char a[PIECES][GPIECE_BYTES];  // matrix A pieces [k-half][128 n-rows][128 B]
+    unsigned char c[PIECES][GPIECE_BYTES];  // centred walker pieces [k-half][128 m-rows][128 B]
+    unsigned long long afull, cfull, cempty, tfull[ACC], tempty[ACC];
+    unsigned tmem_base;
+};
+
+__device__ __forceinline__ unsigned long long smem_desc_sw128(unsigned addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(1024 >> 4) << 32;  // 8 rows x 128 B
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+
+struct GaussParams {
+    long long W;      // points
+    int mtiles;       // ceil(W / 128)
+    long long wpad;   // mtiles * 128: rows per piece in the C piece buffer
+    int d;
+    double lognorm;
+    double *out;      // [W]
+};
+
+__global__ void __launch_bounds__(kGaussThreads, 1)
+gaussian_tc_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapA,
+                   const GaussParams p) {
+    extern __shared__ unsigned char smem_raw[];
+    GaussSmem &sm = *reinterpret_cast<GaussSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        mbar_init(&sm.afull, 1);
+        mbar_init(&sm.cfull, 1);
+        mbar_init(&sm.cempty, 1);
+        for (int a = 0; a < ACC; ++a) {
+            mbar_init(&sm.tfull[a], 1);
+            mbar_init(&sm.tempty[a], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&sm.tmem_base))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const unsigned tmem = sm.tmem_base;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(&sm.afull, PIECES * GPIECE_BYTES);  // the matrix: once per CTA
+            for (int pc = 0; pc < PIECES; ++pc)
+                for (int kh = 0; kh < 2; ++kh)
+                    tma_load_2d(sm.a[pc] + kh * (GPIECE_BYTES / 2), &mapA, kh * 64, pc * GN, &sm.afull);
+            unsigned cphase = 0;
+            for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+                mbar_wait(&sm.cempty, cphase ^ 1);
+                mbar_expect_tx(&sm.cfull, PIECES * GPIECE_BYTES);
+                for (int pc = 0; pc < PIECES; ++pc)
+                    for (int kh = 0; kh < 2; ++kh)
+                        tma_load_2d(sm.c[pc] + kh * (GPIECE_BYTES / 2), &mapC, kh * 64,
+                                    (int)(pc * p.wpad + (long long)mt * BM), &sm.cfull);
+                cphase ^= 1;
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr unsigned idesc = idesc_bf16_f32(BM, GN);
+            // (C piece, A piece): 0 = hi, 1 = mid, 2 = lo; smallest products first
+            const int pc_c[6] = {2, 0, 1, 1, 0, 0};
+            const int pc_a[6] = {0, 2, 1, 0, 1, 0};
+            unsigned cphase = 0, acc = 0, accphase = 0;
+            mbar_wait(&sm.afull, 0);
+            for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+                mbar_wait(&sm.tempty[acc], accphase ^ 1);
+                mbar_wait(&sm.cfull, cphase);
+                cphase ^= 1;
+                tc_fence_after();
+                const unsigned d = tmem + acc * GN;
+#pragma unroll
+                for (int pr = 0; pr < 6; ++pr) {
+                    const unsigned cb = smem_u32(sm.c[pc_c[pr]]), ab = smem_u32(sm.a[pc_a[pr]]);
+#pragma unroll
+                    for (int k = 0; k < GK / 16; ++k) {
+                        const unsigned off = (k >> 2) * (GPIECE_BYTES / 2) + (k & 3) * 32;  // k-half, then 32 B per k-step
+                        tc_mma(d, smem_desc_sw128(cb + off), smem_desc_sw128(ab + off), idesc, (pr | k) ? 1u : 0u);
+                    }
+                }
+                tc_commit(&sm.cempty);
+                tc_commit(&sm.tfull[acc]);
+                if (++acc == ACC) {
+                    acc = 0;
+                    accphase ^= 1;
+                }
+            }
+        }
+    } else {
+        const int quarter = warp & 3;
+        const int row = quarter * 32 + lane;
+        unsigned acc = 0, accphase = 0;
+        for (int mt = blockIdx.x; mt < p.mtiles; mt += gridDim.x) {
+            mbar_wait(&sm.tfull[acc], accphase);
+            tc_fence_after();
+            double ss = 0.0;
+#pragma unroll 1
+            for (int cb = 0; cb < GN; cb += 32) {
+                if (cb >= p.d) break;
+                unsigned v[32];
+                const unsigned taddr = tmem + ((unsigned)(quarter * 32) << 16) + acc * GN + cb;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+                    "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]),
+                      "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+                      "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                float part = 0.0f;  // padded columns are exact zeros (zero rows of the matrix pieces)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float y = __uint_as_float(v[j]);
+                    part = fmaf(y, y, part);
+                }
+                ss += (double)part;
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.tempty[acc]);
+            if (++acc == ACC) {
+                acc = 0;
+                accphase ^= 1;
+            }
+            const long long w = (long long)mt * BM + row;
+            if (w < p.W) p.out[w] = p.lognorm - 0.5 * ss;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
+}
+
+// rows of (X - mu) (FP64, d columns) -> three bf16 pieces, rows padded to wpad, columns to 128.
+// mu == nullptr: no centring (used for the matrix A itself, rows = d).
+__global__ void split_rows128_kernel(const double *__restrict__ X, const double *__restrict__ mu,
+                                     __nv_bfloat16 *__restrict__ out, long long rows, long long rpad, int d) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rpad * GK) return;
+    const long long r = e / GK;
+    const int c = (int)(e % GK);
+    double v = (r < rows && c < d) ? X[r * d + c] - (mu ? mu[c] : 0.0) : 0.0;
+#pragma unroll
+    for (int pc = 0; pc < PIECES; ++pc) {
+        const __nv_bfloat16 h = __double2bfloat16(v);
+        out[(size_t)pc * rpad * GK + e] = h;
+        v -= (double)__bfloat162float(h);
+    }
+}
+
 }  // namespace tc
 }  // namespace kmc

@@ -162,3 +162,34 @@ def test_logistic_tensor_core_sampling(km):
     assert np.all(np.abs(t_tc.mean(0) - t64.mean(0)) < 0.5 * sd)
     assert np.all(np.abs(t_tc.std(0) - sd) < 0.3 * sd)
     assert np.all(np.abs(t_tc.mean(0) - tstar) < 6 * sd + 0.03)
+
+
+# ---------------------------------------------------------------------------------- tcgen05 dense Gaussian (K2)
+
+@pytest.mark.parametrize("d,npts", [(100, 1000), (128, 129), (17, 5), (64, 4096)])
+def test_gaussian_tensor_core_path_matches_fp64(km, d, npts):
+    """Opt-in tcgen05 Mahalanobis GEMM (both operands split into 3 bf16 pieces, 6 piece pairs, FP32
+    accumulation in TMEM).  Stated tolerance against the FP64 kernel: 1e-5 * (1 + |y|^2) absolute."""
+    prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
+    ld = km.LogDensity("gaussian", d, prm)
+    assert ld.info("tensor_cores") == 0.0            # exact FP64 by default
+    pts = np.linspace(-1, 1, d) + np.random.default_rng(0).standard_normal((npts, d)) * 1.5
+    want = ld.eval(pts)
+    ld.set_option("tensor_cores", 1)
+    assert ld.info("tensor_cores") == 1.0
+    got = ld.eval(pts)
+    ss = 2.0 * (prm[-1] - want)
+    assert np.all(np.abs(got - want) <= 1e-5 * (1.0 + ss)), np.max(np.abs(got - want) / (1.0 + ss))
+
+
+def test_gaussian_tensor_core_sampling(km):
+    d, nw = 100, 2048
+    mean, cov = np.linspace(-1, 1, d), cases.spd_cov(d, 3)
+    ld = km.gaussian(mean, cov)
+    ld.set_option("tensor_cores", 1)
+    x0 = mean + cases.ball(np.zeros(d), 1.0, nw, 1)
+    th, ar, lp, _ = km.emcee(ld, x0, niter=600 * nw, nburnin=400 * nw, nthin=20, use_progress_meter=False, seed=2)
+    t, a, _, _ = km.squash_walkers(th, ar)
+    sd = np.sqrt(np.diag(cov))
+    assert a > 0.1
+    assert np.all(np.abs(t.mean(0) - mean) < 0.25 * sd) and np.all(np.abs(t.std(0) - sd) < 0.25 * sd)
