@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--workload", default="rosenbrock2d", choices=sorted(WORKLOADS))
     ap.add_argument("--launch-mode", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--tensor-cores", type=int, default=None, choices=[0, 1],
+                    help="force the tcgen05 (1) or FP64 (0) log-density kernel of the dense plugins")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
     if args.impl == "reference":
@@ -228,6 +230,11 @@ def main():
     ns = (nitw - nbw) // nthin
     params, x0 = make_inputs(wl, 1000 + rank)
     ld = km.LogDensity(wl["plugin"], d, params, data=wl.get("_data"), device=local)
+    if args.tensor_cores is not None:
+        ld.set_option("tensor_cores", args.tensor_cores)
+    elif wl["plugin"] == "gaussian" and d > 16:
+        ld.set_option("tensor_cores", 1)          # bench default for configs[2]: the tcgen05 Mahalanobis GEMM
+    tensor = ld.info("tensor_cores") == 1.0
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -321,12 +328,27 @@ def main():
         tpath = ROOT / "profiles" / "traffic.json"
         if tpath.exists():
             traffic = json.loads(tpath.read_text()).get(args.workload)
+        if wl["plugin"] == "logistic":      # tensor-bound nominally: 2*d*N flops per walker-step
+            peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+            tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+            tflops = 2.0 * d * wl["ndata"] * walker_steps_per_step / (k_ms * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                    "traffic": traffic, "kernel": "tc::logistic_tc_kernel" if tensor else "logistic_logp_kernel",
+                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
+                    "algorithmic_flops_per_step": 2.0 * d * wl["ndata"] * walker_steps_per_step,
+                    "kernel_ms_per_step": k_ms,
+                    "note": "algorithmic flops 2*d*N per walker-step; the tcgen05 kernel issues 3x that (theta split "
+                            "into 3 bf16 pieces) and is bounded by the MUFU softplus epilogue (profiles/r1_summary.md)"}
+        else:
+            roof = None
         line = {
             "metric": METRIC, "value": world * walker_steps_per_step * args.steps / (dev_ms * 1e-3), "unit": UNIT,
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16x3 split operands, f32 accumulate (tcgen05); f64 state" if tensor else "f64",
+            "data": "synthetic",
             "config": {
-                "workload": args.workload, "description": wl["desc"], "plugin": wl["plugin"], "d": d,
+                "workload": args.workload, "tensor_cores": tensor, "description": wl["desc"], "plugin": wl["plugin"], "d": d,
                 "nwalkers_per_gpu": nw, "niter_walker": nitw, "nburnin_walker": nbw, "nthin": nthin,
                 "samples_per_walker": ns, "a_scale": 2.0, "rng": "philox4x32-10",
                 "parallelism": "1 ensemble" if world == 1 else f"{world} independent ensembles (no collective)",
@@ -335,12 +357,15 @@ def main():
                 "l2": "ensemble state is L2-resident by construction across the dependent half-steps of one step; "
                       "L2 flushed (256 MiB fill) between steps, inside the timed region",
             },
-            "roofline": {
+            "roofline": roof or {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel": "emcee_run_kernel",
+                "traffic": traffic, "peak_source": peak_src,
+                "kernel": "emcee_smem_kernel" if d <= 4 else ("emcee_run_kernel" if d <= 16 else
+                          "propose_kernel + gaussian_tc_kernel + accept_kernel" if tensor else
+                          "propose_kernel + gaussian_wide_logp_kernel + accept_kernel"),
                 "algorithmic_bytes_per_launch": alg_bytes_per_step, "kernel_ms_per_launch": k_ms,
-                "note": "algorithmic bytes = (24d+24) per walker-step + (8d+8) per stored sample; the state fits "
-                        "L2, so frac is against the HBM copy peak and may exceed 1",
+                "note": "algorithmic bytes = (24d+24) per walker-step + (8d+8) per stored sample; a state that fits "
+                        "L2 / shared memory makes frac against the HBM copy peak able to exceed 1",
             },
             "e2e": {"value": world * walker_steps_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": int(x0.nbytes),

@@ -134,6 +134,10 @@ int32_t kmc_emcee_nlocal(kmc_sampler_t s, int64_t *nl);
  * nl = nwalkers, or 2*shard_count for a sharded sampler (its slice of half 0, then of half 1). */
 int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp,
                                double *accept_ratio);
+/* Posterior moments of the whole stored chain (all walkers squashed, src/samplers.jl:372-428),
+ * reduced on the device: mean [d], unbiased variance [d], number of samples.  Avoids copying
+ * chains of 10^9+ samples to the host. */
+int32_t kmc_emcee_chain_moments(kmc_sampler_t s, double *mean, double *var, int64_t *count);
 /* Current ensemble: theta [nw][d], logp [nw], naccept [nw]; any may be NULL. */
 int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept);
 

@@ -20,7 +20,7 @@ SYMBOLS = [
     "kmc_density_get_info",
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
     "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
-    "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state",
+    "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state", "kmc_emcee_chain_moments",
 ]
 
 
@@ -72,6 +72,7 @@ lib.kmc_emcee_progress.argtypes = [C.c_void_p, _i64p, _dp, _dp, _i64p]
 lib.kmc_emcee_nsamples.argtypes = [C.c_void_p, _i64p]
 lib.kmc_emcee_copy_results.argtypes = [C.c_void_p, _dp, _dp, _dp]
 lib.kmc_emcee_copy_state.argtypes = [C.c_void_p, _dp, _dp, _i64p]
+lib.kmc_emcee_chain_moments.argtypes = [C.c_void_p, _dp, _dp, _i64p]
 for _name in SYMBOLS:
     if _name not in ("kmc_version", "kmc_last_error"):
         getattr(lib, _name).restype = C.c_int32

@@ -1,0 +1,77 @@
+"""Integrated autocorrelation time and effective sample size of ensemble chains.
+
+Restated from the (commented-out, pre-1.0 and untested) reference code in
+/root/reference/src/analysis.jl:
+    int_acorr    :140-167     acor1d  :252-273 (its text is corrupted by a pasted fragment at :256-262)
+    auto_window  :281-286     eff_samples :88-95
+Nothing in the reference pins these numbers (all of analysis.jl is commented out and has no
+test), so parity is "unpinned"; the known answer used here is AR(1): tau = (1+phi)/(1-phi).
+
+Layout: the reference takes `thetas[ntheta, nsamples, nchains]` (Julia column-major); here chains
+come from emcee as [nchains(=walkers), nsamples(, ntheta)] -- the same memory order.
+"""
+from __future__ import annotations
+
+import warnings
+
+import numpy as np
+
+
+def acor1d(x, norm: bool = True) -> np.ndarray:
+    """Autocorrelation function of one chain via FFT, NO zero padding (circular), first half kept (:252-273)."""
+    x = np.asarray(x, dtype=np.float64)
+    f = np.fft.fft(x - x.mean())
+    acf = np.real(np.fft.ifft(f * np.conj(f)))
+    acf /= 4 * len(x)
+    if norm:
+        acf /= acf[0]
+    return acf[:len(acf) // 2]
+
+
+def auto_window(taus, c) -> int:
+    """First (1-based) index i with i >= c*taus[i], else len-1 (:281-286).  Returns the 1-based index."""
+    for i, t in enumerate(taus, start=1):
+        if i >= c * t:
+            return i
+    return len(taus) - 1
+
+
+def int_acorr(thetas, c=5, warn=True, warnat=50):
+    """Integrated autocorrelation time per parameter, averaged over chains (:140-167).
+
+    thetas: [nchains, nsamples] or [nchains, nsamples, ntheta].
+    Returns (tau[ntheta], converged[ntheta]); converged = nsamples / tau should be > ~50.
+    If anything is NaN both are set to -1 (the reference's "hack")."""
+    assert c > 1
+    th = np.asarray(thetas, dtype=np.float64)
+    if th.ndim == 2:
+        th = th[:, :, None]
+    nchains, nsamples, ntheta = th.shape
+    out = np.empty(ntheta)
+    for n in range(ntheta):
+        rho = np.zeros(nsamples // 2)
+        for cc in range(nchains):
+            rho += acor1d(th[cc, :, n])
+        rho /= nchains
+        taus = 2 * np.cumsum(rho) - 1          # the -1: dfm/emcee issue 267
+        window = auto_window(taus, c)
+        out[n] = taus[window - 1]
+    converged = nsamples / out
+    if warn and np.any(converged < warnat):
+        warnings.warn("Estimate of integrated autocorrelation likely not accurate!")
+    if np.any(np.isnan(out)) or np.any(np.isnan(converged)):
+        out = np.full(ntheta, -1.0)
+        converged = np.full(ntheta, -1.0)
+    return out, converged
+
+
+def eff_samples(thetas, c=5):
+    """(Neff, suggested thinning, mean convergence, Neff per theta, tau per theta, convergence per theta) (:88-95)."""
+    th = np.asarray(thetas, dtype=np.float64)
+    if th.ndim == 2:
+        th = th[:, :, None]
+    nchains, nsamples, _ = th.shape
+    acorr, converged = int_acorr(th, c=c, warn=False)
+    ns = nsamples / acorr * nchains
+    return (int(round(ns.mean())), int(round(nsamples * nchains // ns.mean())), float(converged.mean()),
+            np.round(ns).astype(int), acorr, converged)

@@ -201,6 +201,12 @@ class Sampler:
         check(lib.kmc_emcee_copy_results(self._h, _ptr(th), _ptr(lp), _ptr(ar)))
         return th, lp, ar
 
+    def chain_moments(self):
+        """(mean[d], var[d], nsamples) of the whole stored chain, reduced on the device."""
+        mean, var, n = np.empty(self.d), np.empty(self.d), C.c_int64()
+        check(lib.kmc_emcee_chain_moments(self._h, _ptr(mean), _ptr(var), C.byref(n)))
+        return mean, var, n.value
+
     def state(self):
         x, lp, na = np.empty((self.nw, self.d)), np.empty(self.nw), np.empty(self.nw, dtype=np.int64)
         check(lib.kmc_emcee_copy_state(self._h, _ptr(x), _ptr(lp), _ptr(na, _i64p)))

@@ -1008,6 +1008,34 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
     return KMC_OK;
 }
 
+int32_t kmc_emcee_chain_moments(kmc_sampler_t s, double *mean, double *var, int64_t *count) {
+    if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
+    const long long nrows = s->ns * s->nl;
+    const int d = s->d;
+    if (count) *count = nrows;
+    if (nrows < 1) return fail(KMC_ERR_STATE, "no samples stored");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    double *sums = nullptr;
+    CU_TRY(dev_alloc(&sums, sizeof(double) * 2 * d, s->opts.device));
+    std::vector<double> h(2 * d), shift(d);
+    cudaError_t e = cudaMemsetAsync(sums, 0, sizeof(double) * 2 * d, s->stream);
+    if (e == cudaSuccess) {
+        const unsigned grid = (unsigned)std::min<long long>((nrows * d + 255) / 256, 148 * 8);
+        kmc::chain_moments_kernel<<<grid, 256, sizeof(double) * 2 * d, s->stream>>>(s->chain_x, nrows, d, sums);
+        e = cudaMemcpyAsync(h.data(), sums, sizeof(double) * 2 * d, cudaMemcpyDeviceToHost, s->stream);
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(shift.data(), s->chain_x, sizeof(double) * d, cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    dev_free(sums);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "chain moments failed: %s", cudaGetErrorString(e));
+    const double n = (double)nrows;
+    for (int c = 0; c < d; ++c) {
+        if (mean) mean[c] = shift[c] + h[c] / n;
+        if (var) var[c] = nrows > 1 ? (h[d + c] - h[c] * h[c] / n) / (n - 1.0) : 0.0;
+    }
+    return KMC_OK;
+}
+
 int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept) {
     if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
     CU_TRY(cudaSetDevice(s->opts.device));

@@ -448,6 +448,25 @@ __global__ void chain_transpose_kernel(const double *__restrict__ in, double *__
     }
 }
 
+// Posterior moments of the stored chain on the device (the squash_walkers + mean/var reduction
+// of src/samplers.jl:372-428 + test/runtests.jl:36-43 without copying the chain to the host):
+// per component, sum and sum of squares of (x - shift), shift = the first stored sample.
+__global__ void __launch_bounds__(256) chain_moments_kernel(const double *__restrict__ chain, long long nrows, int d,
+                                                            double *__restrict__ sums /* [2][d] */) {
+    extern __shared__ double sh[];  // [2][d]
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sh[c] = 0.0;
+    __syncthreads();
+    const long long total = nrows * d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(e % d);
+        const double v = chain[e] - chain[c];
+        atomicAdd(&sh[c], v);
+        atomicAdd(&sh[d + c], v * v);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) atomicAdd(&sums[c], sh[c]);
+}
+
 // K5: accept-counter statistics of the progress display (src/samplers.jl:276-278).
 __global__ void nacc_sum_kernel(const unsigned *__restrict__ nacc, long long nw, unsigned long long *sum) {
     unsigned long long s = 0;

@@ -14,6 +14,10 @@ if len(sys.argv) > 4:
     wl = dict(wl, nw=int(sys.argv[4]))
 params, x0 = bench.make_inputs(wl, 1)
 ld = km.LogDensity(wl["plugin"], wl["d"], params, data=wl.get("_data"))
+import os
+if os.environ.get("KMC_TC") is not None:
+    ld.set_option("tensor_cores", int(os.environ["KMC_TC"]))
+print("tensor_cores:", ld.info("tensor_cores"))
 for rep in range(3):
     s = km.Sampler(ld, x0, iters, iters // 2, max(1, iters // 4), 2.0, seed=rep, launch_mode=mode)
     s.run(-1)

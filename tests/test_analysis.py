@@ -1,0 +1,64 @@
+"""int_acorr / acor1d / auto_window / eff_samples (reference: commented code in src/analysis.jl).
+Known answer: an AR(1) process x_t = phi x_{t-1} + e_t has tau = (1+phi)/(1-phi)."""
+import numpy as np
+import pytest
+
+
+def _ar1(phi, nchains, n, seed):
+    rng = np.random.default_rng(seed)
+    x = np.zeros((nchains, n))
+    e = rng.standard_normal((nchains, n))
+    x[:, 0] = e[:, 0] / np.sqrt(1 - phi * phi)
+    for t in range(1, n):
+        x[:, t] = phi * x[:, t - 1] + e[:, t]
+    return x
+
+
+@pytest.mark.parametrize("phi", [0.0, 0.5, 0.9])
+def test_int_acorr_ar1(km, phi):
+    x = _ar1(phi, 64, 20000, 1)
+    tau, conv = km.int_acorr(x, warn=False)
+    want = (1 + phi) / (1 - phi)
+    assert tau.shape == (1,) and abs(tau[0] - want) < 0.08 * want + 0.05
+    assert conv[0] == pytest.approx(20000 / tau[0])
+
+
+def test_acor1d_and_window(km):
+    x = _ar1(0.7, 1, 4096, 2)[0]
+    rho = km.acor1d(x)
+    assert len(rho) == 2048 and rho[0] == pytest.approx(1.0) and abs(rho[1] - 0.7) < 0.05
+    un = km.acor1d(x, norm=False)
+    assert un[0] == pytest.approx(np.sum((x - x.mean()) ** 2) / (4 * len(x)))     # the reference's /(4 n) scaling
+    assert km.auto_window(np.array([3.0, 3.0, 3.0, 0.5, 0.1]), 1.5) == 4          # first 1-based i >= c*tau_i
+    assert km.auto_window(np.array([9.0, 9.0, 9.0]), 5) == 2                      # none -> len-1
+
+
+def test_int_acorr_multi_theta_nan_and_warning(km):
+    x = np.stack([_ar1(0.5, 8, 5000, 3), _ar1(0.8, 8, 5000, 4)], axis=-1)
+    tau, conv = km.int_acorr(x, warn=False)
+    assert tau.shape == (2,) and abs(tau[0] - 3) < 0.5 and abs(tau[1] - 9) < 1.5
+    neff, thin, mconv, neffs, taus, convs = km.eff_samples(x)
+    assert np.array_equal(taus, tau) and neff == int(round((5000 / tau * 8).mean()))
+    bad = x.copy()
+    bad[0, 0, 0] = np.nan
+    t2, c2 = km.int_acorr(bad, warn=False)
+    assert np.all(t2 == -1) and np.all(c2 == -1)
+    with pytest.warns(UserWarning):
+        km.int_acorr(_ar1(0.99, 4, 400, 5))        # far too short: nsamples/tau < 50
+
+
+@pytest.mark.gpu
+def test_int_acorr_of_emcee_chains_and_moment_errors(km):
+    """Free-running statistical check of north_star: posterior moments within Monte Carlo error,
+    with the error bar taken from the integrated autocorrelation time of the chains themselves."""
+    mean, cov = [0.5, -0.25], [[0.47, 1.8], [1.8, 7.0]]
+    ld = km.gaussian(mean, cov)
+    nw = 256
+    x0 = km.make_theta0s(np.array([0.4, 0.3]), 0.1, ld, nw, seed=1)
+    th, ar, lp, _ = km.emcee(ld, x0, niter=4000 * nw, nburnin=1000 * nw, use_progress_meter=False, seed=2)
+    tau, conv = km.int_acorr(th, warn=False)
+    assert np.all(tau > 1) and np.all(tau < 60) and np.all(conv > 50)
+    neff = th.shape[0] * th.shape[1] / tau
+    sd = np.sqrt(np.diag(cov))
+    err = sd / np.sqrt(neff)
+    assert np.all(np.abs(th.reshape(-1, 2).mean(0) - mean) < 6 * err + 1e-3)

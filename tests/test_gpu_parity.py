@@ -233,3 +233,17 @@ def test_full_size_properties_config2(km):
     x2, l2, na2 = s2.state()
     s2.close()
     assert np.array_equal(xf, x2) and np.array_equal(lf, l2) and np.array_equal(na, na2)
+
+
+def test_device_chain_moments(km):
+    """kmc_emcee_chain_moments == numpy mean / var (ddof=1) of the squashed chain."""
+    ld = km.gaussian([0.5, -0.25], [[0.47, 1.8], [1.8, 7.0]])
+    s = km.Sampler(ld, cases.ball([0.4, 0.3], 0.1, 1000, 2), 300, 100, 2, 2.0, 5)
+    s.run(-1)
+    mean, var, n = s.chain_moments()
+    th, _, ar = s.results()
+    s.close()
+    t, _, _, _ = km.squash_walkers(th, ar)
+    assert n == len(t) == 1000 * 100
+    np.testing.assert_allclose(mean, t.mean(0), rtol=1e-11, atol=1e-12)
+    np.testing.assert_allclose(var, t.var(0, ddof=1), rtol=1e-10)
