@@ -72,6 +72,8 @@ def test_logistic_eval_and_validation(km, orc):
     ld = km.logistic(X, y, prior_sigma=10.0)
     od = orc.Density("logistic", 32, [10.0], data=np.concatenate([X.ravel(), y]))
     pts = tstar + 0.05 * np.random.default_rng(2).standard_normal((70, 32))
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=0, atol=2e-3)     # default: tcgen05 path
+    ld.set_option("tensor_cores", 0)                                              # exact FP64 kernel
     np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-10)
     with pytest.raises(km.KmcError):
         km.LogDensity("logistic", 32, [10.0])                       # no data
