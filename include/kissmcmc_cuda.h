@@ -117,6 +117,15 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters);
  * run alternates kmc_emcee_run_half(s, 1) with the exchange of the just-updated half. */
 int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps);
 int32_t kmc_emcee_sync(kmc_sampler_t s);
+/* Peer mode (sharded ensemble, one process per GPU on one NVLink/NVSwitch node): instead of an
+ * all-gather after every half-step, each rank's persistent kernel gathers partner rows directly
+ * from the owner GPU's memory and the ranks meet at a flag barrier in peer memory per half-step.
+ * kmc_emcee_ipc_export writes two 64-byte CUDA IPC handles (positions, flags); the caller
+ * exchanges them (e.g. torch.distributed.all_gather) and passes all ranks' handles, rank-major,
+ * to kmc_emcee_set_peers.  Then every rank calls kmc_emcee_run concurrently. */
+int32_t kmc_emcee_ipc_export(kmc_sampler_t s, void *handle_x, void *handle_flags);
+int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *handles_flags, int32_t nranks,
+                            int32_t rank);
 /* Device pointers of the ensemble state (x: [nw][d] FP64, logp: [nw] FP64, naccept: [nw] u32),
  * valid until kmc_emcee_destroy; for stream-ordered exchanges by the caller. */
 int32_t kmc_emcee_device_ptrs(kmc_sampler_t s, void **x, void **logp, void **naccept);

@@ -19,7 +19,7 @@ SYMBOLS = [
     "kmc_density_create", "kmc_density_destroy", "kmc_density_eval", "kmc_density_set_option",
     "kmc_density_get_info",
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
-    "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
+    "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_ipc_export", "kmc_emcee_set_peers", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
     "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state", "kmc_emcee_chain_moments",
 ]
 
@@ -67,6 +67,8 @@ lib.kmc_emcee_sync.argtypes = [C.c_void_p]
 lib.kmc_emcee_run_half.argtypes = [C.c_void_p, C.c_int64]
 lib.kmc_emcee_device_ptrs.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]
 lib.kmc_emcee_nlocal.argtypes = [C.c_void_p, _i64p]
+lib.kmc_emcee_ipc_export.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+lib.kmc_emcee_set_peers.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
 lib.kmc_emcee_last_run_ms.argtypes = [C.c_void_p, _dp, _i64p]
 lib.kmc_emcee_progress.argtypes = [C.c_void_p, _i64p, _dp, _dp, _i64p]
 lib.kmc_emcee_nsamples.argtypes = [C.c_void_p, _i64p]

@@ -178,6 +178,17 @@ class Sampler:
     def sync(self):
         check(lib.kmc_emcee_sync(self._h))
 
+    def ipc_export(self):
+        """(handle_x, handle_flags): two 64-byte CUDA IPC handles for peer mode."""
+        hx, hf = C.create_string_buffer(64), C.create_string_buffer(64)
+        check(lib.kmc_emcee_ipc_export(self._h, hx, hf))
+        return hx.raw, hf.raw
+
+    def set_peers(self, handles_x, handles_flags, rank: int):
+        """All ranks' IPC handles (lists of 64-byte strings, rank-major)."""
+        n = len(handles_x)
+        check(lib.kmc_emcee_set_peers(self._h, b"".join(handles_x), b"".join(handles_flags), n, rank))
+
     def device_ptrs(self):
         """(x, logp, naccept) device addresses: x [nw][d] f64, logp [nw] f64, naccept [nw] u32."""
         x, lp, na = C.c_void_p(), C.c_void_p(), C.c_void_p()

@@ -106,6 +106,7 @@ void dev_free(void *p) {
 // ------------------------------------------------------------------ kernel registry
 struct Ops {
     const void *run[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [replay][smem-resident state]
+    const void *run_peer = nullptr;  // general kernel with cross-GPU partner gathers (Philox mode)
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
     int block = 0;               // max threads per CTA of the run kernels
     int min_blocks = 1;          // CTAs per SM the kernels are compiled for
@@ -120,6 +121,7 @@ Ops make_ops() {
     Ops o;
     o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
     o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
+    o.run_peer = (const void *)kmc::emcee_run_kernel<Dn, D, false, true>;
     if (D <= 4) {  // shared-memory-resident variant for small rows
         o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;
         o.run[1][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), true>;
@@ -415,6 +417,13 @@ struct kmc_sampler_s {
     bool use_smem = false;           // owned state is shared-memory resident (emcee_smem_kernel)
     unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
     kmc::BatchBuf bb{};                     // batched plugins: proposals of the active shard
+    // peer mode
+    int npeers = 0, rank = 0;
+    const double *peer_x[8] = {};
+    unsigned long long *peer_flags[8] = {};
+    unsigned long long *flags = nullptr;    // this rank's flag array [8]
+    unsigned long long epoch = 0;
+    std::vector<void *> ipc_opened;
     BatchScratch bsc;
 };
 
@@ -621,6 +630,8 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     dev_free(s->rp_z);
     dev_free(s->rp_u);
     dev_free(s->scratch);
+    for (void *q : s->ipc_opened) cudaIpcCloseMemHandle(q);
+    cudaFree(s->flags);
     dev_free(s->bb.Y);
     dev_free(s->bb.z);
     dev_free(s->bb.u);
@@ -691,6 +702,8 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     CU_TRY_S(dev_alloc(&s->nacc, sizeof(unsigned) * s->nw, opts->device));
     CU_TRY_S(dev_alloc(&s->barrier, sizeof(unsigned long long), opts->device));
     CU_TRY_S(dev_alloc(&s->scratch, 4 * sizeof(unsigned long long), opts->device));
+    CU_TRY_S(cudaMalloc(&s->flags, 8 * sizeof(unsigned long long)));  // own allocation: exported through CUDA IPC
+    CU_TRY_S(cudaMemsetAsync(s->flags, 0, 8 * sizeof(unsigned long long), s->stream));
     if (s->ns > 0) {
         CU_TRY_S(dev_alloc(&s->chain_x, sizeof(double) * s->ns * s->nl * d, opts->device));
         CU_TRY_S(dev_alloc(&s->chain_lp, sizeof(double) * s->ns * s->nl, opts->device));
@@ -736,7 +749,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         };
         bool fits = false;
         s->use_smem = false;
-        if (opts->launch_mode == 0 && density->ops.run[r][1]) {  // shared-memory-resident state if it fits
+        if (opts->launch_mode == 0 && density->ops.run[r][1] && opts->shard_count == 0) {  // shared-memory-resident state if it fits
             int max_optin = 0;
             CU_TRY_S(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opts->device));
             const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, 2, density->ops.smem_per_walker, fits);
@@ -849,6 +862,18 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
 
     void *args[] = {&p, s->dn->params.data()};
     p.per_cta = s->per_cta;
+    const bool peer = s->npeers > 1;
+    if (peer) {
+        if (replay || s->dn->ops.batch || s->opts.launch_mode != 0 || !s->dn->ops.run_peer)
+            return fail(KMC_ERR_UNSUPPORTED, "peer mode needs a fused (non-batched) plugin, Philox draws and launch_mode 0");
+        for (int r = 0; r < s->npeers; ++r) {
+            p.peer_x[r] = s->peer_x[r];
+            p.peer_flags[r] = s->peer_flags[r];
+        }
+        p.npeers = s->npeers;
+        p.rank = s->rank;
+        p.epoch_base = s->epoch;
+    }
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
     if (s->dn->ops.batch) {  // propose -> batched log-density -> accept, per half-step
         const unsigned grid = (unsigned)((s->scnt * 32 + 255) / 256);
@@ -874,11 +899,12 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
             ++s->last_launches;
         }
     } else {
-        const void *kern = s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
+        const void *kern = peer ? s->dn->ops.run_peer : s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
         set_range(hbeg, hend);
         CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(s->block), args,
-                                           s->use_smem ? s->smem_bytes : 0, s->stream));
-        s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid;
+                                           (!peer && s->use_smem) ? s->smem_bytes : 0, s->stream));
+        s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid * (peer ? 2 : 1);
+        if (peer) s->epoch += (unsigned long long)(hend - hbeg - 1);
         ++s->last_launches;
     }
     CU_TRY(cudaEventRecord(s->ev1, s->stream));
@@ -891,6 +917,43 @@ int32_t kmc_emcee_run(kmc_sampler_t s, int64_t niters) {
     if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
     if (s->hdone & 1) return fail(KMC_ERR_STATE, "an outer iteration is half done: finish it with kmc_emcee_run_half");
     return kmc_emcee_run_half(s, niters < 0 ? -1 : 2 * niters);
+}
+
+int32_t kmc_emcee_ipc_export(kmc_sampler_t s, void *handle_x, void *handle_flags) {
+    if (!s || !handle_x || !handle_flags) return fail(KMC_ERR_INVALID, "NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_x), s->x));
+    CU_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_flags), s->flags));
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *handles_flags, int32_t nranks,
+                            int32_t rank) {
+    if (!s || !handles_x || !handles_flags) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(KMC_ERR_INVALID, "bad rank / nranks (max 8)");
+    if (s->scnt * nranks != s->nhalf || s->sbeg != (long long)rank * s->scnt)
+        return fail(KMC_ERR_INVALID, "peer mode needs equal shards: rank r owns [r*S, (r+1)*S) of each half");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    const cudaIpcMemHandle_t *hx = reinterpret_cast<const cudaIpcMemHandle_t *>(handles_x);
+    const cudaIpcMemHandle_t *hf = reinterpret_cast<const cudaIpcMemHandle_t *>(handles_flags);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            s->peer_x[r] = s->x;
+            s->peer_flags[r] = s->flags;
+            continue;
+        }
+        void *px = nullptr, *pf = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&px, hx[r], cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(px);
+        CU_TRY(cudaIpcOpenMemHandle(&pf, hf[r], cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(pf);
+        s->peer_x[r] = static_cast<const double *>(px);
+        s->peer_flags[r] = static_cast<unsigned long long *>(pf);
+    }
+    s->npeers = nranks;
+    s->rank = rank;
+    return KMC_OK;
 }
 
 int32_t kmc_emcee_device_ptrs(kmc_sampler_t s, void **x, void **logp, void **naccept) {

@@ -59,6 +59,12 @@ struct RunParams {
     unsigned lemire_t;      // (2^32 - nhalf) mod nhalf
     unsigned long long *barrier;  // grid barrier arrival counter (monotonic)
     unsigned long long bar_base;  // its value when this launch starts
+    // peer mode (one ensemble sharded over GPUs): partner rows are gathered straight from the
+    // owner GPU's memory over NVLink and ranks meet at a system-scope flag barrier per half-step
+    const double *peer_x[8];          // x of every rank (own rank: the local pointer)
+    unsigned long long *peer_flags[8];  // flag array [npeers] of every rank
+    int npeers, rank;
+    unsigned long long epoch_base;    // cross-GPU barrier epochs completed before this launch
 };
 
 // ------------------------------------------------------------------ grid barrier
@@ -162,12 +168,45 @@ __device__ __forceinline__ void chain_store(const RunParams &p, size_t o, bool a
     __stcs(p.chain_lp + o, acc ? p1 : lpk);
 }
 
+// ------------------------------------------------------------------ cross-GPU pieces (peer mode)
+// Partner rows that may live on another GPU: system-scope relaxed loads, never from L1.
+template <int D>
+__device__ __forceinline__ void load_row_sys(const double *p, double (&v)[D]) {
+    if constexpr (D % 2 == 0) {
+#pragma unroll
+        for (int c = 0; c < D; c += 2)
+            asm volatile("ld.relaxed.sys.global.v2.f64 {%0, %1}, [%2];" : "=d"(v[c]), "=d"(v[c + 1]) : "l"(p + c) : "memory");
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v[c]) : "l"(p + c) : "memory");
+    }
+}
+
+// Called by ONE CTA between two local grid barriers: publish "this GPU finished epoch e" into
+// every rank's flag array (st.release.sys after the local barrier made all CTAs' writes visible
+// to this thread: cumulativity carries them system-wide), then wait for every rank's flag.
+__device__ __forceinline__ void cross_gpu_barrier(const RunParams &p, unsigned long long epoch) {
+    if ((int)threadIdx.x < p.npeers) {
+        unsigned long long *dst = p.peer_flags[threadIdx.x] + p.rank;
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(epoch) : "memory");
+        const unsigned long long *mine = p.peer_flags[p.rank] + threadIdx.x;
+        const long long t0 = clock64();
+        unsigned long long v;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(mine) : "memory");
+            if (v < epoch && clock64() - t0 > 20000000000LL) __trap();  // ~10 s watchdog: a missing peer must not hang the GPU
+        } while (v < epoch);
+    }
+}
+
 // ------------------------------------------------------------------ general kernel
 // Owned state stays in L2/HBM; any ensemble size.  U walkers in flight per thread.
-template <template <int> class Dn, int D, bool REPLAY>
+template <template <int> class Dn, int D, bool REPLAY, bool PEER = false>
 __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_kernel(const RunParams p,
                                                                                     const Dn<D> dn) {
     constexpr int U = in_flight<D>();
+    const unsigned shard_size = p.shard_end - p.shard_begin;
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
     const unsigned base = p.shard_begin + blockIdx.x * p.per_cta;  // first owned position (in each half)
     const unsigned cnt = base >= p.shard_end ? 0u : min(p.per_cta, p.shard_end - base);
@@ -208,7 +247,12 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                 const unsigned l = tid + (g + q) * nthr;
                 if (l < cnt) {
                     const size_t k = (size_t)a0 + base + l;
-                    load_row_cg<D>(p.x + (size_t)dr[q].j * D, xj[q]);
+                    if constexpr (PEER) {  // the partner's owner: position inside its half / shard size
+                        const unsigned pos = dr[q].j >= p.nhalf ? dr[q].j - p.nhalf : dr[q].j;
+                        load_row_sys<D>(p.peer_x[pos / shard_size] + (size_t)dr[q].j * D, xj[q]);
+                    } else {
+                        load_row_cg<D>(p.x + (size_t)dr[q].j * D, xj[q]);
+                    }
                     load_row<D>(p.x + k * D, xk[q]);
                     lpk[q] = p.lp[k];
                 }
@@ -259,6 +303,18 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
             if (gridDim.x > 1) {
                 if (tid == 0) barrier_wait(p.barrier, target);
                 __syncthreads();
+            }
+            if constexpr (PEER) {  // every GPU has finished the half-step before anyone gathers from it
+                if (blockIdx.x == 0) cross_gpu_barrier(p, p.epoch_base + (unsigned long long)(h - p.h0) + 1);
+                target += gridDim.x;
+                __syncthreads();
+                if (gridDim.x > 1) {
+                    if (tid == 0) {
+                        barrier_arrive(p.barrier);
+                        barrier_wait(p.barrier, target);
+                    }
+                    __syncthreads();
+                }
             }
         }
     }

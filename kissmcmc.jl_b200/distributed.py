@@ -59,11 +59,16 @@ def _gather_numpy(local: np.ndarray, group=None):
 
 
 def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=2.0, seed=0, group=None,
-                  sampler_factory=None, x_view=None):
+                  sampler_factory=None, x_view=None, exchange="allgather"):
     """emcee (src/samplers.jl:188-216) of one ensemble sharded over the ranks of `group`.
 
     Every rank passes the SAME theta0s ([nw] or [nw, d]).  Returns the reference 4-tuple for
-    the WHOLE ensemble on every rank.  sampler_factory / x_view are test seams (CPU fakes)."""
+    the WHOLE ensemble on every rank.  sampler_factory / x_view are test seams (CPU fakes).
+
+    exchange="allgather": one launch per half-step + NCCL all-gather of the updated half.
+    exchange="peer":      ONE persistent kernel per rank; partner rows are gathered straight from
+                          the owner GPU's memory over NVLink (CUDA IPC) and the ranks meet at a
+                          flag barrier in peer memory per half-step -- no collective at all."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     th = np.asarray(theta0s, dtype=np.float64)
     scalar_theta = th.ndim == 1
@@ -80,6 +85,27 @@ def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=
 
     import contextlib
     ctx = contextlib.nullcontext()
+    if sampler_factory is None and exchange == "peer":
+        _require_plugin(logdensity)
+        s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, launch_mode=0,
+                    shard=(begin, count))
+        try:
+            hx, hf = s.ipc_export()
+            allh = [None] * world
+            dist.all_gather_object(allh, (hx, hf), group=group)
+            s.set_peers([h[0] for h in allh], [h[1] for h in allh], rank)
+            dist.barrier(group)                 # every rank's initial state is in place
+            s.run(-1, sync=True)                # the kernels of all ranks synchronise among themselves
+            dist.barrier(group)                 # nobody tears its memory down while a peer still reads it
+            lth, llp, lar = s.results()
+        finally:
+            s.close()
+        thetas = assemble_shards(_gather_numpy(lth, group), nwalkers)
+        logp = assemble_shards(_gather_numpy(llp, group), nwalkers)
+        ratio = assemble_shards(_gather_numpy(lar, group), nwalkers)
+        if scalar_theta:
+            thetas = thetas[:, :, 0]
+        return thetas, ratio, logp, None
     if sampler_factory is None:
         _require_plugin(logdensity)
         s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, launch_mode=1,

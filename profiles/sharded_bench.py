@@ -14,11 +14,36 @@ if world > 1:
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 lg = int(sys.argv[1]) if len(sys.argv) > 1 else 24
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 20
+mode = sys.argv[3] if len(sys.argv) > 3 else "allgather"
 wl = dict(bench.WORKLOADS["gaussian10d"], nw=1 << lg)
 params, x0 = bench.make_inputs(wl, 1)
 nw, d, nhalf = wl["nw"], wl["d"], wl["nw"] // 2
 ld = km.LogDensity("gaussian", d, params, device=local)
 begin, count = kd.shard_range(nw, rank, world)
+if mode == "peer":
+    s = km.Sampler(ld, x0, iters + 4, 0, 10**6, 2.0, 7, launch_mode=0, shard=(begin, count), device=local)
+    if world > 1:
+        hx, hf = s.ipc_export()
+        allh = [None] * world
+        dist.all_gather_object(allh, (hx, hf))
+        s.set_peers([h[0] for h in allh], [h[1] for h in allh], rank)
+        dist.barrier()
+    s.run(4, sync=True)                       # warm-up: 4 iterations
+    if world > 1: dist.barrier()
+    torch.cuda.synchronize()
+    s.run(iters, sync=True)
+    ms_k, _ = s.last_run_ms()
+    ms = torch.tensor([ms_k], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.barrier()
+    if rank == 0:
+        print(json.dumps({"mode": "sharded-peer", "n_gpus": world, "nwalkers": nw, "d": d, "iters": iters,
+                          "ms_per_halfstep": ms.item() / (2 * iters), "walker_steps_per_s": nw * iters / (ms.item() * 1e-3)}))
+    s.close()
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
 s = km.Sampler(ld, x0, iters + 4, 0, 10**6, 2.0, 7, launch_mode=1, shard=(begin, count), device=local)
 st = torch.cuda.Stream()
 s.set_stream(st.cuda_stream)

@@ -156,7 +156,7 @@ def test_independent_two_ranks(orc):
 
 # ---------------------------------------------------------------------------------- GPU (NCCL)
 
-def _gpu_worker(rank, world, port, q):
+def _gpu_worker(rank, world, port, q, exchange="allgather"):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -164,21 +164,25 @@ def _gpu_worker(rank, world, port, q):
     try:
         ld = km.LogDensity("gaussian", 10, cases.plugin_specs()["mvn10"][2], device=rank)
         x0 = cases.ball(np.zeros(10), 0.1, 4096, 3)
-        out = km.distributed.emcee_sharded(ld, x0, niter=30 * 4096, nburnin=10 * 4096, nthin=5, seed=11)
+        out = km.distributed.emcee_sharded(ld, x0, niter=30 * 4096, nburnin=10 * 4096, nthin=5, seed=11,
+                                           exchange=exchange)
         q.put((rank, out[0], out[1], out[2]))
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.gpu
-def test_sharded_two_gpus_equals_one_gpu(km):
-    """One ensemble over 2 GPUs (NCCL all-gather of the updated half per half-step) == 1 GPU, bit for bit."""
+@pytest.mark.parametrize("exchange", ["allgather", "peer"])
+def test_sharded_two_gpus_equals_one_gpu(km, exchange):
+    """One ensemble over 2 GPUs == 1 GPU, bit for bit: with an NCCL all-gather of the updated half per
+    half-step, and with the fused peer mode (partner rows gathered over NVLink inside one persistent
+    kernel per rank, flag barrier in peer memory)."""
     if km.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_gpu_worker, args=(r, 2, port, q, exchange)) for r in range(2)]
     [p.start() for p in procs]
     res = sorted([q.get(timeout=300) for _ in range(2)], key=lambda t: t[0])
     [p.join(60) for p in procs]
