@@ -756,7 +756,21 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
             s->use_smem = fits && rounds <= (unsigned)kmc::kRounds && s->smem_bytes <= (size_t)max_optin;
         }
         if (!s->use_smem) {
-            geometry(density->ops.run[r][0], density->ops.block, density->ops.min_blocks, 0, fits);
+            int occ = 0;  // as many CTAs per SM as the kernel's registers allow (at least what it was compiled for)
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, density->ops.run[r][0], density->ops.block, 0) != cudaSuccess) {
+                cudaGetLastError();
+                occ = 0;
+            }
+            if (opts->shard_count > 0 && density->ops.run_peer) {  // a sharded sampler may switch to the peer kernel
+                int occ_p = 0;
+                if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_p, density->ops.run_peer, density->ops.block, 0) !=
+                    cudaSuccess) {
+                    cudaGetLastError();
+                    occ_p = 0;
+                }
+                occ = std::min(occ, occ_p);
+            }
+            geometry(density->ops.run[r][0], density->ops.block, std::max(occ, 1), 0, fits);
             if (!fits) return bail(fail(KMC_ERR_CUDA, "kernel does not fit on the device"));
         }
     }

@@ -182,6 +182,39 @@ __device__ __forceinline__ void load_row_sys(const double *p, double (&v)[D]) {
     }
 }
 
+// One bulk (TMA) copy of a whole partner row, global/peer -> shared: a single D*8-byte request on
+// the wire instead of D/2 16-byte loads; completion is counted on a CTA mbarrier.
+__device__ __forceinline__ void bulk_row_g2s(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void kbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void kbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void kbar_wait(unsigned long long *bar, unsigned parity) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    const long long t0 = clock64();
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (!done && clock64() - t0 > 20000000000LL) __trap();
+    }
+}
+
 // Called by ONE CTA between two local grid barriers: publish "this GPU finished epoch e" into
 // every rank's flag array (st.release.sys after the local barrier made all CTAs' writes visible
 // to this thread: cumulativity carries them system-wide), then wait for every rank's flag.
@@ -207,6 +240,15 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                                                                                     const Dn<D> dn) {
     constexpr int U = in_flight<D>();
     const unsigned shard_size = p.shard_end - p.shard_begin;
+    // peer mode: partner rows land in shared memory through bulk copies (rows of 16-byte multiples)
+    constexpr bool BULK = PEER && (D % 2 == 0);
+    __shared__ __align__(16) double prow[BULK ? U * max_threads<D>() * D : 1];
+    __shared__ unsigned long long pbar;
+    unsigned pphase = 0;
+    if constexpr (BULK) {
+        if (threadIdx.x == 0) kbar_init(&pbar, 1);
+        __syncthreads();
+    }
     const unsigned tid = threadIdx.x, nthr = blockDim.x;
     const unsigned base = p.shard_begin + blockIdx.x * p.per_cta;  // first owned position (in each half)
     const unsigned cnt = base >= p.shard_end ? 0u : min(p.per_cta, p.shard_end - base);
@@ -242,6 +284,17 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                 }
             }
             double xj[U][D], xk[U][D], lpk[U];
+            if constexpr (BULK) {  // bytes this CTA's bulk copies of the group will deliver
+                if (tid == 0) {
+                    unsigned rows = 0;
+#pragma unroll
+                    for (int q = 0; q < U; ++q) {
+                        const unsigned first = (g + q) * nthr;
+                        rows += first < cnt ? min(nthr, cnt - first) : 0u;
+                    }
+                    kbar_expect_tx(&pbar, rows * D * 8);
+                }
+            }
 #pragma unroll
             for (int q = 0; q < U; ++q) {  // all gathers and owned rows of the group in flight together
                 const unsigned l = tid + (g + q) * nthr;
@@ -249,13 +302,28 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
                     const size_t k = (size_t)a0 + base + l;
                     if constexpr (PEER) {  // the partner's owner: position inside its half / shard size
                         const unsigned pos = dr[q].j >= p.nhalf ? dr[q].j - p.nhalf : dr[q].j;
-                        load_row_sys<D>(p.peer_x[pos / shard_size] + (size_t)dr[q].j * D, xj[q]);
+                        const double *src = p.peer_x[pos / shard_size] + (size_t)dr[q].j * D;
+                        if constexpr (BULK) bulk_row_g2s(prow + ((size_t)q * nthr + tid) * D, src, D * 8, &pbar);
+                        else load_row_sys<D>(src, xj[q]);
                     } else {
                         load_row_cg<D>(p.x + (size_t)dr[q].j * D, xj[q]);
                     }
                     load_row<D>(p.x + k * D, xk[q]);
                     lpk[q] = p.lp[k];
                 }
+            }
+            if constexpr (BULK) {
+                kbar_wait(&pbar, pphase);
+                pphase ^= 1;
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const unsigned l = tid + (g + q) * nthr;
+                    if (l < cnt) {
+#pragma unroll
+                        for (int c = 0; c < D; ++c) xj[q][c] = prow[((size_t)q * nthr + tid) * D + c];
+                    }
+                }
+                __syncthreads();  // the row buffers are reused by the next group's bulk copies
             }
 #pragma unroll
             for (int q = 0; q < U; ++q) {
