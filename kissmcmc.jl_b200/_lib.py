@@ -6,10 +6,11 @@ every compute call fails with KmcError when no CUDA device is present.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libkissmcmc_cuda.so"
+LIB_PATH = Path(os.environ["KMC_LIB"]) if os.environ.get("KMC_LIB") else PKG / "libkissmcmc_cuda.so"
 
 MODE_PHILOX, MODE_REPLAY = 0, 1
 

@@ -752,7 +752,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         if (opts->launch_mode == 0 && density->ops.run[r][1] && opts->shard_count == 0) {  // shared-memory-resident state if it fits
             int max_optin = 0;
             CU_TRY_S(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, opts->device));
-            const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, 2, density->ops.smem_per_walker, fits);
+            const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, kmc::kSmemCtas, density->ops.smem_per_walker, fits);
             s->use_smem = fits && rounds <= (unsigned)kmc::kRounds && s->smem_bytes <= (size_t)max_optin;
         }
         if (!s->use_smem) {

@@ -391,14 +391,26 @@ __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_k
 // ------------------------------------------------------------------ shared-memory-resident kernel
 // x / logp / accept counters of the CTA's walkers live in shared memory for the whole launch;
 // global x is only written on accept (so partners can gather it) and logp / counters are
-// written back once at the end.  Every thread owns at most kRounds walker positions of each
+// written back once at the end.  Geometry (threads x rounds x CTAs per SM) was swept on a B200 for
+// the 2^20-walker config: 384x5x2 7.36 us per half-step, 448x4x2 7.54, 512x4x2 7.52, 320x6x2 7.48,
+// 896x4x1 8.01, 640x6x1 8.12, 256x7x3 10.4.  Every thread owns at most kRounds walker positions of each
 // half: slot(half b, round q) = b*per_cta + q*blockDim + tid.  Layout (L = 2*per_cta slots),
 // component-major so that a warp's accesses are conflict-free:
 //   double xs[D][L]; double lps[L]; unsigned naccs[L];
 // Per half-step: the draws (Philox) of all rounds were made in the previous barrier's shadow;
 // partner rows are prefetched two rounds ahead.
-constexpr int kRounds = 4;
-constexpr int kSmemThreads = 448;
+#ifndef KMC_SMEM_ROUNDS
+#define KMC_SMEM_ROUNDS 5
+#endif
+#ifndef KMC_SMEM_THREADS
+#define KMC_SMEM_THREADS 384
+#endif
+#ifndef KMC_SMEM_CTAS
+#define KMC_SMEM_CTAS 2
+#endif
+constexpr int kRounds = KMC_SMEM_ROUNDS;
+constexpr int kSmemThreads = KMC_SMEM_THREADS;
+constexpr int kSmemCtas = KMC_SMEM_CTAS;  // CTAs per SM the kernel is compiled and launched for
 
 // Shared memory through explicit 32-bit addresses: every access is (per-thread base) +
 // (warp-uniform offset), so a thread keeps ONE address register for all of its slots.
@@ -420,7 +432,7 @@ __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
 }
 
 template <template <int> class Dn, int D, bool REPLAY>
-__global__ void __launch_bounds__(kSmemThreads, 2) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
+__global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned nthr = blockDim.x;
     const unsigned L = 2 * p.per_cta;
