@@ -16,6 +16,7 @@
 #include "../../include/kissmcmc_cuda.h"
 #include "kmc_batched.cuh"
 #include "kmc_tc.cuh"
+#include "kmc_fused_gauss.cuh"
 #include "kmc_kernels.cuh"
 
 namespace {
@@ -312,39 +313,51 @@ cudaError_t batch_scratch_reserve(BatchScratch &sc, const kmc_density_s &dn, lon
     return e;
 }
 
+cudaError_t gauss_pieces_reserve(BatchScratch &sc, const kmc_density_s &dn, long long npts) {
+    const long long wpad = ((npts + kmc::tc::BM - 1) / kmc::tc::BM) * kmc::tc::BM;
+    const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)wpad * kmc::tc::GK;
+    if (pneed <= sc.pieces_bytes) return cudaSuccess;
+    dev_free(sc.pieces);
+    sc.pieces = nullptr;
+    sc.pieces_bytes = 0;
+    cudaError_t e = dev_alloc(&sc.pieces, pneed, dn.device);
+    if (e == cudaSuccess) sc.pieces_bytes = pneed;
+    return e;
+}
+
+// The tcgen05 Mahalanobis GEMM on centred bf16 pieces [3][wpad][128] already in sc.pieces.
+cudaError_t launch_gauss_tc(const kmc_density_s &dn, BatchScratch &sc, long long npts, double *out, cudaStream_t st) {
+    const int d = dn.d;
+    kmc::tc::GaussParams gp{};
+    gp.W = npts;
+    gp.mtiles = (int)((npts + kmc::tc::BM - 1) / kmc::tc::BM);
+    gp.wpad = (long long)gp.mtiles * kmc::tc::BM;
+    gp.d = d;
+    gp.lognorm = dn.params[d + (size_t)d * d];
+    gp.out = out;
+    CUtensorMap mapC;
+    if (!make_map_bf16_k128(&mapC, sc.pieces, (unsigned long long)kmc::tc::PIECES * gp.wpad, kmc::tc::BM))
+        return cudaErrorInvalidValue;
+    const size_t smem = sizeof(kmc::tc::GaussSmem) + 1024;
+    cudaError_t e = cudaFuncSetAttribute(kmc::tc::gaussian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return e;
+    const unsigned grid = (unsigned)std::min<long long>(gp.mtiles, dn.nsm);
+    kmc::tc::gaussian_tc_kernel<<<grid, kmc::tc::kGaussThreads, smem, st>>>(mapC, dn.mapA, gp);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long long npts, double *out,
                               BatchScratch &sc, cudaStream_t st) {
     const int d = dn.d;
     if (dn.ops.batch == 1 && dn.tc_ok && dn.tc_on) {  // tcgen05 Mahalanobis GEMM
-        kmc::tc::GaussParams gp{};
-        gp.W = npts;
-        gp.mtiles = (int)((npts + kmc::tc::BM - 1) / kmc::tc::BM);
-        gp.wpad = (long long)gp.mtiles * kmc::tc::BM;
-        gp.d = d;
-        gp.lognorm = dn.params[d + (size_t)d * d];
-        gp.out = out;
-        const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)gp.wpad * kmc::tc::GK;
-        if (pneed > sc.pieces_bytes) {
-            dev_free(sc.pieces);
-            sc.pieces = nullptr;
-            sc.pieces_bytes = 0;
-            cudaError_t e = dev_alloc(&sc.pieces, pneed, dn.device);
-            if (e != cudaSuccess) return e;
-            sc.pieces_bytes = pneed;
-        }
-        const long long ne = gp.wpad * kmc::tc::GK;
-        kmc::tc::split_rows128_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, dn.d_params, sc.pieces, npts,
-                                                                                    gp.wpad, d);
-        CUtensorMap mapC;
-        if (!make_map_bf16_k128(&mapC, sc.pieces, (unsigned long long)kmc::tc::PIECES * gp.wpad, kmc::tc::BM))
-            return cudaErrorInvalidValue;
-        const size_t smem = sizeof(kmc::tc::GaussSmem) + 1024;
-        cudaError_t e = cudaFuncSetAttribute(kmc::tc::gaussian_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)smem);
+        cudaError_t e = gauss_pieces_reserve(sc, dn, npts);
         if (e != cudaSuccess) return e;
-        const unsigned grid = (unsigned)std::min<long long>(gp.mtiles, dn.nsm);
-        kmc::tc::gaussian_tc_kernel<<<grid, kmc::tc::kGaussThreads, smem, st>>>(mapC, dn.mapA, gp);
-        return cudaGetLastError();
+        const long long wpad = ((npts + kmc::tc::BM - 1) / kmc::tc::BM) * kmc::tc::BM;
+        const long long ne = wpad * kmc::tc::GK;
+        kmc::tc::split_rows128_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, dn.d_params, sc.pieces, npts,
+                                                                                    wpad, d);
+        return launch_gauss_tc(dn, sc, npts, out, st);
     }
     if (dn.ops.batch == 1) {
         const int dp = d | 1;
@@ -636,6 +649,7 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     dev_free(s->bb.z);
     dev_free(s->bb.u);
     dev_free(s->bb.p1);
+    dev_free(s->bb.j);
     dev_free(s->bsc.part);
     dev_free(s->bsc.pieces);
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -717,6 +731,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         CU_TRY_S(dev_alloc(&s->bb.z, sizeof(double) * s->scnt, opts->device));
         CU_TRY_S(dev_alloc(&s->bb.u, sizeof(double) * s->scnt, opts->device));
         CU_TRY_S(dev_alloc(&s->bb.p1, sizeof(double) * s->scnt, opts->device));
+        CU_TRY_S(dev_alloc(&s->bb.j, sizeof(unsigned) * s->scnt, opts->device));
     } else {
         long long nwl = s->nw;
         void *args[] = {&s->x, &s->lp, &nwl, density->params.data()};
@@ -891,9 +906,49 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
     if (s->dn->ops.batch) {  // propose -> batched log-density -> accept, per half-step
         const unsigned grid = (unsigned)((s->scnt * 32 + 255) / 256);
+        const bool gtc = s->dn->ops.batch == 1 && s->dn->tc_ok && s->dn->tc_on;  // Y-free tcgen05 Gaussian pipeline
+        if (gtc && s->opts.launch_mode == 0) {  // K2F: the whole range of half-steps in one persistent fused kernel
+            kmc::tc::FusedParams fpar{};
+            fpar.mu = s->dn->d_params;
+            fpar.lognorm = s->dn->params[s->d + (size_t)s->d * s->d];
+            fpar.d = s->d;
+            const size_t smem = sizeof(kmc::tc::FusedSmem) + 1024;
+            const void *kern = replay ? (const void *)kmc::tc::gaussian_fused_kernel<true>
+                                      : (const void *)kmc::tc::gaussian_fused_kernel<false>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long ntiles = (s->scnt + kmc::tc::BM - 1) / kmc::tc::BM;
+            const unsigned fgrid = (unsigned)std::min<long long>(ntiles, s->dn->nsm);
+            set_range(hbeg, hend);
+            void *fargs[] = {(void *)&s->dn->mapA, &p, &fpar};
+            CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(fgrid), dim3(kmc::tc::kFusedThreads), fargs, smem, s->stream));
+            s->bar_base += (unsigned long long)(hend - hbeg - 1) * fgrid;
+            s->last_launches += 1;
+            CU_TRY(cudaEventRecord(s->ev1, s->stream));
+            s->timed = true;
+            s->hdone = hend;
+            return KMC_OK;
+        }
+        if (gtc) CU_TRY(gauss_pieces_reserve(s->bsc, *s->dn, s->scnt));
+        const long long wpad = ((s->scnt + kmc::tc::BM - 1) / kmc::tc::BM) * kmc::tc::BM;
+        const unsigned gridp = (unsigned)((wpad * 32 + 255) / 256);
         for (long long h = hbeg; h < hend; ++h) {
             set_range(h, h + 1);
             const int store = (p.n0 > 0 && p.phase0 == 0) ? 1 : 0;
+            if (gtc) {
+                if (replay)
+                    kmc::propose_pieces_kernel<true><<<gridp, 256, 0, s->stream>>>(p, s->bb, h, s->d, s->dn->d_params,
+                                                                                   s->bsc.pieces, wpad);
+                else
+                    kmc::propose_pieces_kernel<false><<<gridp, 256, 0, s->stream>>>(p, s->bb, h, s->d, s->dn->d_params,
+                                                                                    s->bsc.pieces, wpad);
+                CU_TRY(launch_gauss_tc(*s->dn, s->bsc, s->scnt, s->bb.p1, s->stream));
+                if (replay)
+                    kmc::accept_recompute_kernel<true><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d, p.n0, store, p.sidx0);
+                else
+                    kmc::accept_recompute_kernel<false><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d, p.n0, store, p.sidx0);
+                s->last_launches += 3;
+                continue;
+            }
             if (replay) kmc::propose_kernel<true><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d);
             else kmc::propose_kernel<false><<<grid, 256, 0, s->stream>>>(p, s->bb, h, s->d);
             CU_TRY(launch_batch_logp(*s->dn, s->bb.Y, s->scnt, s->bb.p1, s->bsc, s->stream));

@@ -11,6 +11,8 @@
 //
 // The same density kernels serve kmc_density_eval (initial p0s :209, make_theta0s :334-338).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "kmc_kernels.cuh"
 
 namespace kmc {
@@ -20,6 +22,7 @@ struct BatchBuf {
     double *z;    // [W]
     double *u;    // [W]
     double *p1;   // [W] log-density of the proposals
+    unsigned *j;  // [W] partner index (global), kept for the recomputing accept stage
 };
 
 // One warp per active walker; lanes stride over the components (coalesced row access).
@@ -73,6 +76,84 @@ __global__ void __launch_bounds__(256) accept_kernel(const RunParams p, const Ba
         const size_t o = chain_row(p, sidx, batch, i);
         for (int c = lane; c < d; c += 32) __stcs(p.chain_x + o * d + c, acc ? y[c] : xk[c]);
         if (lane == 0) __stcs(p.chain_lp + o, acc ? p1 : p0);
+    }
+}
+
+// Variants for the tcgen05 Gaussian path: the proposal is never written in FP64.  propose emits the
+// centred proposal (y - mu) already split into three bf16 pieces [3][wpad][128] (what the GEMM's
+// TMA loads); accept recomputes y = xj + z(xk - xj) -- the same three IEEE operations, so the same
+// bits -- only for accepted walkers (and for the chain store).  Saves the Y write, the Y read of a
+// separate split kernel and the Y read of accept: ~230 MB -> ~120 MB per half-step at d = 100.
+template <bool REPLAY>
+__global__ void __launch_bounds__(256) propose_pieces_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+                                                             const double *__restrict__ mu,
+                                                             __nv_bfloat16 *__restrict__ pieces, long long wpad) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= wpad) return;
+    const unsigned W = p.shard_end - p.shard_begin;
+    const size_t plane = (size_t)wpad * 128;
+    __nv_bfloat16 *row = pieces + (size_t)w * 128;
+    if (w >= W) {  // padding rows of the last tile
+        for (int c = lane; c < 128; c += 32)
+            for (int pc = 0; pc < 3; ++pc) row[pc * plane + c] = __float2bfloat16(0.0f);
+        return;
+    }
+    const unsigned i = p.shard_begin + w;
+    const unsigned batch = (unsigned)(h & 1);
+    unsigned j;
+    double z, u;
+    step_draws<REPLAY>(p, h, i, j, z, u);
+    const double *xk = p.x + ((size_t)(batch ? p.nhalf : 0u) + i) * d;
+    const double *xj = p.x + (size_t)j * d;
+    for (int c = lane; c < 128; c += 32) {
+        double v = 0.0;
+        if (c < d) v = dadd(xj[c], dmul(z, dsub(xk[c], xj[c]))) - mu[c];  // :255, centred
+#pragma unroll
+        for (int pc = 0; pc < 3; ++pc) {
+            const __nv_bfloat16 hb = __double2bfloat16(v);
+            row[pc * plane + c] = hb;
+            v -= (double)__bfloat162float(hb);
+        }
+    }
+    if (lane == 0) {
+        b.z[w] = z;
+        b.u[w] = u;
+        b.j[w] = j;
+    }
+}
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(256) accept_recompute_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+                                                               long long n, int store, long long sidx) {
+    const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const unsigned W = p.shard_end - p.shard_begin;
+    if (w >= W) return;
+    const unsigned i = p.shard_begin + w;
+    const unsigned batch = (unsigned)(h & 1);
+    const size_t k = (size_t)(batch ? p.nhalf : 0u) + i;
+    const double p1 = b.p1[w], p0 = p.lp[k], z = b.z[w];
+    const bool acc = accept_exact<false>(p.nm1, z, p1, p0, b.u[w]);  // :260
+    double *xk = p.x + k * d;
+    const double *xj = p.x + (size_t)b.j[w] * d;
+    const size_t o = store ? chain_row(p, sidx, batch, i) : 0;
+    if (acc || store) {
+        for (int c = lane; c < d; c += 32) {
+            const double xo = xk[c];
+            const double v = acc ? dadd(xj[c], dmul(z, dsub(xo, xj[c]))) : xo;  // :255 again, same bits
+            if (acc) xk[c] = v;                                                  // :261
+            if (store) __stcs(p.chain_x + o * d + c, v);                         // :268-272
+        }
+    }
+    if (lane == 0) {
+        if (acc) {
+            p.lp[k] = p1;
+            p.nacc[k] += 1u;
+        }
+        if (batch == 1 && n == 0) {
+            p.nacc[i] = 0u;
+            p.nacc[(size_t)p.nhalf + i] = 0u;
+        }
+        if (store) __stcs(p.chain_lp + o, acc ? p1 : p0);
     }
 }
 

@@ -195,3 +195,50 @@ def test_gaussian_tensor_core_sampling(km):
     sd = np.sqrt(np.diag(cov))
     assert a > 0.1
     assert np.all(np.abs(t.mean(0) - mean) < 0.25 * sd) and np.all(np.abs(t.std(0) - sd) < 0.25 * sd)
+
+
+def test_gaussian_tensor_core_pipeline_states_exact(km, orc):
+    """The Y-free tcgen05 pipeline (propose emits bf16 pieces, accept recomputes y for accepted walkers):
+    in replay mode every decision whose margin is above the tensor path's log-density error agrees with
+    the oracle, and then the states -- recomputed with the same three IEEE operations -- are bit-identical."""
+    d, nw, nitw, nbw, nthin = 40, 200, 9, 0, 1
+    prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
+    ld, od = km.LogDensity("gaussian", d, prm), orc.Density("gaussian", d, prm)
+    ld.set_option("tensor_cores", 1)
+    x0 = cases.ball(np.zeros(d), 0.5, nw, 5)
+    want = orc.emcee(od, x0, nitw, nbw, nthin, 2.0, seed=21, trace=True, nthreads=4)
+    s = km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, 21, km.MODE_REPLAY)
+    s.set_replay(*want["trace"][:3])
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    same = na == want["naccept"]
+    assert same.mean() > 0.98                      # only near-tie decisions may differ
+    if same.all():
+        assert np.array_equal(th, want["chain_x"]) and np.array_equal(x, want["x"])
+        ss = 2.0 * (prm[-1] - want["chain_lp"])
+        assert np.all(np.abs(lp - want["chain_lp"]) <= 1e-5 * (1.0 + ss))
+
+
+def test_gaussian_fused_kernel_equals_three_kernel_pipeline(km):
+    """K2F (one persistent fused tcgen05 kernel, launch_mode 0) == propose / GEMM / accept kernels
+    (launch_mode 1): same bf16 pieces, same MMA order, same epilogue -> bit-identical chains.
+    Sizes exercise partial tiles (nw/2 not a multiple of 128), several tiles per CTA and odd d."""
+    for d, nw in ((100, 2 * 1000), (33, 2 * 130), (64, 2 * 128 * 150)):
+        prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
+        ld = km.LogDensity("gaussian", d, prm)
+        ld.set_option("tensor_cores", 1)
+        x0 = np.linspace(-1, 1, d) + cases.ball(np.zeros(d), 0.7, nw, 5)
+        out = []
+        for mode in (0, 1):
+            s = km.Sampler(ld, x0, 8, 3, 2, 2.0, 77, launch_mode=mode)
+            s.run(3)
+            s.run(-1)
+            th, lp, ar = s.results()
+            x, l, na = s.state()
+            s.close()
+            out.append((th, lp, ar, x, l, na))
+        for a, b in zip(*out):
+            assert np.array_equal(a, b)
+        assert 0.02 < out[0][2].mean() < 0.9
