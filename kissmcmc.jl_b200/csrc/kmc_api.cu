@@ -891,7 +891,7 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
 
     void *args[] = {&p, s->dn->params.data()};
     p.per_cta = s->per_cta;
-    const bool peer = s->npeers > 1;
+    const bool peer = s->npeers >= 1;  // set_peers was called (a single rank exercises the bulk-copy gathers alone)
     if (peer) {
         if (replay || s->dn->ops.batch || s->opts.launch_mode != 0 || !s->dn->ops.run_peer)
             return fail(KMC_ERR_UNSUPPORTED, "peer mode needs a fused (non-batched) plugin, Philox draws and launch_mode 0");

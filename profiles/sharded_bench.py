@@ -28,6 +28,9 @@ if mode == "peer":
         dist.all_gather_object(allh, (hx, hf))
         s.set_peers([h[0] for h in allh], [h[1] for h in allh], rank)
         dist.barrier()
+    elif os.environ.get("KMC_BULK1"):
+        hx, hf = s.ipc_export()
+        s.set_peers([hx], [hf], 0)
     s.run(4, sync=True)                       # warm-up: 4 iterations
     if world > 1: dist.barrier()
     torch.cuda.synchronize()
