@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -108,6 +109,8 @@ void dev_free(void *p) {
 struct Ops {
     const void *run[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [replay][smem-resident state]
     const void *run_peer = nullptr;  // general kernel with cross-GPU partner gathers (Philox mode)
+    const void *run_bulk[2] = {nullptr, nullptr};  // [peer] bulk (TMA) general kernel, Philox mode, even D >= 6
+    size_t bulk_smem = 0;
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
     int block = 0;               // max threads per CTA of the run kernels
     int min_blocks = 1;          // CTAs per SM the kernels are compiled for
@@ -123,6 +126,11 @@ Ops make_ops() {
     o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
     o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
     o.run_peer = (const void *)kmc::emcee_run_kernel<Dn, D, false, true>;
+    if constexpr (D % 2 == 0 && D >= 6) {
+        o.run_bulk[0] = (const void *)kmc::emcee_bulk_kernel<Dn, D, false>;
+        o.run_bulk[1] = (const void *)kmc::emcee_bulk_kernel<Dn, D, true>;
+        o.bulk_smem = (size_t)3 * kmc::kBulkThreads * D * 8 + 16;
+    }
     if (D <= 4) {  // shared-memory-resident variant for small rows
         o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;
         o.run[1][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), true>;
@@ -428,6 +436,7 @@ struct kmc_sampler_s {
     unsigned grid = 1, per_cta = 1, block = 32;  // persistent launch geometry
     size_t smem_bytes = 0;
     bool use_smem = false;           // owned state is shared-memory resident (emcee_smem_kernel)
+    bool use_bulk = false;           // bulk (TMA) general kernel (emcee_bulk_kernel)
     unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
     kmc::BatchBuf bb{};                     // batched plugins: proposals of the active shard
     // peer mode
@@ -770,7 +779,28 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
             const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, kmc::kSmemCtas, density->ops.smem_per_walker, fits);
             s->use_smem = fits && rounds <= (unsigned)kmc::kRounds && s->smem_bytes <= (size_t)max_optin;
         }
-        if (!s->use_smem) {
+        s->use_bulk = !s->use_smem && opts->launch_mode == 0 && r == 0 && density->ops.run_bulk[0] &&
+                      !getenv("KMC_NO_BULK");
+        if (s->use_bulk) {  // 2 CTAs x 256 threads per SM, rows staged through shared memory
+            const void *kb0 = density->ops.run_bulk[0], *kb1 = density->ops.run_bulk[1];
+            cudaFuncSetAttribute(kb0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density->ops.bulk_smem);
+            cudaFuncSetAttribute(kb1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density->ops.bulk_smem);
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kb1, kmc::kBulkThreads, density->ops.bulk_smem) !=
+                    cudaSuccess || occ < 1) {
+                cudaGetLastError();
+                s->use_bulk = false;
+            } else {
+                const long long want = (s->scnt + kmc::kBulkThreads - 1) / kmc::kBulkThreads;
+                s->grid = (unsigned)std::min<long long>(want, (long long)occ * s->nsm);
+                s->per_cta = (unsigned)((s->scnt + s->grid - 1) / s->grid);
+                s->per_cta = ((s->per_cta + 1) / 2) * 2;  // even: group bases stay 16-byte aligned for any even D
+                s->grid = (unsigned)((s->scnt + s->per_cta - 1) / s->per_cta);
+                s->block = kmc::kBulkThreads;
+                s->smem_bytes = density->ops.bulk_smem;
+            }
+        }
+        if (!s->use_smem && !s->use_bulk) {
             int occ = 0;  // as many CTAs per SM as the kernel's registers allow (at least what it was compiled for)
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, density->ops.run[r][0], density->ops.block, 0) != cudaSuccess) {
                 cudaGetLastError();
@@ -968,10 +998,12 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
             ++s->last_launches;
         }
     } else {
-        const void *kern = peer ? s->dn->ops.run_peer : s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
+        const void *kern = s->use_bulk ? s->dn->ops.run_bulk[peer ? 1 : 0]
+                           : peer      ? s->dn->ops.run_peer
+                                       : s->dn->ops.run[replay ? 1 : 0][s->use_smem ? 1 : 0];
         set_range(hbeg, hend);
         CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(s->grid), dim3(s->block), args,
-                                           (!peer && s->use_smem) ? s->smem_bytes : 0, s->stream));
+                                           (s->use_bulk || (!peer && s->use_smem)) ? s->smem_bytes : 0, s->stream));
         s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid * (peer ? 2 : 1);
         if (peer) s->epoch += (unsigned long long)(hend - hbeg - 1);
         ++s->last_launches;
