@@ -247,3 +247,44 @@ def test_device_chain_moments(km):
     assert n == len(t) == 1000 * 100
     np.testing.assert_allclose(mean, t.mean(0), rtol=1e-11, atol=1e-12)
     np.testing.assert_allclose(var, t.var(0, ddof=1), rtol=1e-10)
+
+
+@pytest.mark.parametrize("plugin,d", [("exponential", 2), ("exponential", 4), ("exponential", 5), ("exponential", 6),
+                                      ("exponential", 8), ("exponential", 16), ("gaussian", 3), ("gaussian", 4),
+                                      ("gaussian", 5), ("gaussian", 6), ("gaussian", 8), ("gaussian", 12),
+                                      ("gaussian", 16)])
+def test_every_compiled_dimension_matches_oracle(km, orc, plugin, d):
+    """Every (plugin, d) instantiation, on every kernel family it can take -- shared-memory kernel
+    (d <= 4, small ensembles), bulk/TMA kernel (even d >= 6, Philox), general kernel (odd d, replay,
+    one launch per half-step) -- bit-identical to the oracle in Philox and replay mode."""
+    if plugin == "exponential":
+        params, x0 = [], np.abs(cases.ball(np.full(d, 1.0), 0.3, 600, d))
+    else:
+        params = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, d))
+        x0 = cases.ball(np.zeros(d), 0.5, 600, d)
+    ld, od = km.LogDensity(plugin, d, params), orc.Density(plugin, d, params)
+    want = orc.emcee(od, x0, 14, 5, 3, 2.0, seed=31 + d, trace=True, nthreads=4)
+    assert want["min_margin"] > 1e-11
+    for kw in (dict(), dict(launch_mode=1), dict(replay=want["trace"][:3])):
+        got = _run_gpu(km, ld, x0, 14, 5, 3, 2.0, seed=31 + d, **kw)
+        _assert_same(got, want)
+
+
+def test_large_ensemble_general_kernels(km, orc):
+    """Ensembles too large for the shared-memory kernel: 2-D Rosenbrock with 2^21 walkers (general kernel)
+    and a 10-D Gaussian with 2^18 walkers (bulk kernel, several groups per CTA, partial last group) agree
+    with one-launch-per-half-step runs and, on a sub-sampled oracle check, with the plugin itself."""
+    ld = km.rosenbrock()
+    x0 = cases.ball([0, 0], 0.1, 1 << 21, 9)
+    a = _run_gpu(km, ld, x0, 6, 2, 2, 2.0, seed=3)
+    b = _run_gpu(km, ld, x0, 6, 2, 2, 2.0, seed=3, launch_mode=1)
+    _assert_same(a, b)
+    prm = cases.gaussian_params(np.linspace(-1, 1, 10), cases.spd_cov(10, 1))
+    ld = km.LogDensity("gaussian", 10, prm)
+    x0 = cases.ball(np.zeros(10), 0.3, (1 << 18) + 2 * 77, 4)
+    a = _run_gpu(km, ld, x0, 6, 2, 2, 2.0, seed=5)
+    b = _run_gpu(km, ld, x0, 6, 2, 2, 2.0, seed=5, launch_mode=1)
+    _assert_same(a, b)
+    od = orc.Density("gaussian", 10, prm)
+    sub = slice(0, None, 997)
+    assert np.array_equal(od.eval(a["x"][sub]), a["lp"][sub])
