@@ -191,3 +191,57 @@ def test_sharded_two_gpus_equals_one_gpu(km, exchange):
     th, ar, lp, _ = km.emcee(ld, x0, niter=30 * 4096, nburnin=10 * 4096, nthin=5, seed=11, use_progress_meter=False)
     for rank, sth, sar, slp in res:
         assert np.array_equal(sth, th) and np.array_equal(slp, lp) and np.array_equal(sar, ar)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case,nw", [("mvn10", 4096), ("rosenbrock", 2048), ("exponential3", 600)])
+def test_two_shards_on_one_gpu_equal_unsharded(km, case, nw):
+    """The sharded-ensemble logic exercised on ONE GPU: two samplers own the two halves of each
+    half-ensemble; after every half-step the updated slices are exchanged by device copies (what the
+    all-gather does across GPUs).  Global walker ids key the Philox draws, so the result is bit-identical
+    to the unsharded run."""
+    name, d, params, th0, rad = cases.plugin_specs()[case]
+    ld = km.LogDensity(name, d, params)
+    x0 = cases.ball(th0, rad, nw, 3)
+    if name == "exponential":
+        x0 = np.abs(x0)
+    nitw, nbw, nthin = 12, 4, 2
+    th, ar, lp, _ = km.emcee(ld, x0, niter=nitw * nw, nburnin=nbw * nw, nthin=nthin, seed=19, use_progress_meter=False)
+    nhalf, S = nw // 2, nw // 4
+    ss = [km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, 19, launch_mode=1, shard=km.distributed.shard_range(nw, r, 2))
+          for r in range(2)]
+    xs = [km.distributed.x_tensor(s) for s in ss]
+    for h in range(2 * nitw):
+        for s in ss:
+            s.run_half(1, sync=True)
+        lo = (h & 1) * nhalf
+        xs[0][lo + S:lo + 2 * S].copy_(xs[1][lo + S:lo + 2 * S])      # rank 1's slice -> rank 0
+        xs[1][lo:lo + S].copy_(xs[0][lo:lo + S])                      # rank 0's slice -> rank 1
+        torch.cuda.synchronize()
+    parts = [s.results() for s in ss]
+    [s.close() for s in ss]
+    got_th = km.distributed.assemble_shards([p[0] for p in parts], nw)
+    got_lp = km.distributed.assemble_shards([p[1] for p in parts], nw)
+    got_ar = km.distributed.assemble_shards([p[2] for p in parts], nw)
+    assert np.array_equal(got_th, th) and np.array_equal(got_lp, lp) and np.array_equal(got_ar, ar)
+
+
+@pytest.mark.gpu
+def test_single_rank_peer_mode_equals_plain(km):
+    """Peer mode with one rank runs the cross-GPU code path alone (bulk-copy gathers through the
+    peer pointer table, flag barrier on its own flags): bit-identical to the plain run."""
+    name, d, params, th0, rad = cases.plugin_specs()["mvn10"]
+    ld = km.LogDensity(name, d, params)
+    x0 = cases.ball(th0, rad, 20000, 3)
+    out = []
+    for peer in (False, True):
+        s = km.Sampler(ld, x0, 10, 4, 2, 2.0, 5, shard=(0, 10000))
+        if peer:
+            hx, hf = s.ipc_export()
+            s.set_peers([hx], [hf], 0)
+        s.run(3)
+        s.run(-1)
+        out.append(s.results() + s.state())
+        s.close()
+    for a, b in zip(*out):
+        assert np.array_equal(a, b)
