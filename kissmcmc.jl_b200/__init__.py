@@ -9,11 +9,11 @@ from ._lib import KmcError, MODE_PHILOX, MODE_REPLAY, SYMBOLS, LIB_PATH, device_
 from .api import (LogDensity, Sampler, ball_randn, emcee, exponential, gaussian, gaussian_params, logistic, lognormal,
                   make_theta0s, philox4x32_10, rosenbrock, squash_walkers)
 
-from .analysis import acor1d, auto_window, eff_samples, int_acorr  # noqa: E402
+from .analysis import acor1d, auto_window, eff_samples, evaluate_convergence, int_acorr  # noqa: E402
 from . import distributed  # noqa: E402  (multi-GPU drivers; imports torch)
 
 __all__ = [
-    "distributed", "int_acorr", "acor1d", "auto_window", "eff_samples",
+    "distributed", "int_acorr", "acor1d", "auto_window", "eff_samples", "evaluate_convergence",
     "emcee", "make_theta0s", "squash_walkers", "LogDensity", "Sampler", "exponential", "rosenbrock", "gaussian",
     "gaussian_params", "lognormal", "logistic", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "ball_randn",
     "philox4x32_10", "SYMBOLS", "LIB_PATH", "lib",

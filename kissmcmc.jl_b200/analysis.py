@@ -75,3 +75,32 @@ def eff_samples(thetas, c=5):
     ns = nsamples / acorr * nchains
     return (int(round(ns.mean())), int(round(nsamples * nchains // ns.mean())), float(converged.mean()),
             np.round(ns).astype(int), acorr, converged)
+
+
+def evaluate_convergence(*ensembles, c=5):
+    """R-hat (potential scale reduction, should be < 1.1), total effective sample size and average
+    thinning factor from two or more SEPARATE emcee runs (the reference only has the docstring of
+    this function, src/analysis.jl:59-77: "needs input from two separate emcee runs", because the
+    walkers inside one ensemble are not independent; Gelman et al. 2014, p. 281-287).
+
+    Each argument is one run's chains [nwalkers, nsamples(, ntheta)] -- e.g. the per-rank results of
+    distributed.emcee_independent.  Every ensemble is reduced to its walker-mean time series split
+    in two halves (split R-hat); effective sample size and thinning come from eff_samples of all
+    walkers of all runs."""
+    runs = []
+    for th in ensembles:
+        th = np.asarray(th, dtype=np.float64)
+        runs.append(th[:, :, None] if th.ndim == 2 else th)
+    assert len(runs) >= 2, "R-hat needs at least two independent ensembles"
+    n = min(r.shape[1] for r in runs) // 2
+    chains = []
+    for r in runs:                       # chain = all samples of one half of one run, [walkers*n, ntheta]
+        chains.append(r[:, :n].reshape(-1, r.shape[2]))
+        chains.append(r[:, n:2 * n].reshape(-1, r.shape[2]))
+    m, L = len(chains), chains[0].shape[0]
+    means = np.stack([ch.mean(0) for ch in chains])
+    W = np.stack([ch.var(0, ddof=1) for ch in chains]).mean(0)
+    B = L * means.var(0, ddof=1)
+    rhat = np.sqrt(((L - 1) / L * W + B / L) / W)
+    neff, nthin, _, _, _, _ = eff_samples(np.concatenate([r[:, :2 * n] for r in runs], axis=0), c=c)
+    return rhat, neff, nthin

@@ -62,3 +62,26 @@ def test_int_acorr_of_emcee_chains_and_moment_errors(km):
     sd = np.sqrt(np.diag(cov))
     err = sd / np.sqrt(neff)
     assert np.all(np.abs(th.reshape(-1, 2).mean(0) - mean) < 6 * err + 1e-3)
+
+
+def test_evaluate_convergence_rhat(km):
+    """R-hat ~ 1 for runs of the same stationary process, >> 1.1 when one run sits elsewhere."""
+    a, b = _ar1(0.6, 32, 4000, 7), _ar1(0.6, 32, 4000, 8)
+    rhat, neff, nthin = km.evaluate_convergence(a, b)
+    assert rhat.shape == (1,) and abs(rhat[0] - 1) < 0.02 and neff > 10000 and 2 <= nthin <= 8
+    rhat_bad, _, _ = km.evaluate_convergence(a, b + 3.0)
+    assert rhat_bad[0] > 1.5
+    with pytest.raises(AssertionError):
+        km.evaluate_convergence(a)
+
+
+@pytest.mark.gpu
+def test_rhat_of_two_independent_gpu_ensembles(km):
+    ld = km.rosenbrock()
+    runs = []
+    for seed in (1, 2):
+        x0 = km.make_theta0s(np.array([0.0, 0.0]), 0.1, ld, 512, seed=seed)
+        th, ar, _, _ = km.emcee(ld, x0, niter=6000 * 512, nburnin=2000 * 512, nthin=4, seed=seed, use_progress_meter=False)
+        runs.append(th)
+    rhat, neff, nthin = km.evaluate_convergence(*runs)
+    assert np.all(rhat < 1.1) and neff > 1000
