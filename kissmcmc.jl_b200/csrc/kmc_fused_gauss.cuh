@@ -33,9 +33,9 @@ struct __align__(1024) FusedSmem {
     unsigned char c[PIECES][GPIECE_BYTES];  // centred proposal pieces (A operand) of the current tile
     unsigned long long afull, mma_done;
     unsigned tmem_base;
-    double z[BM], u[BM], p1[BM];
-    unsigned j[BM];
-    unsigned char acc[BM];
+    double z[2][BM], u[2][BM];   // per-row draws, double-buffered by tile parity (P3 of tile t overlaps P1 of tile t+1)
+    unsigned j[2][BM];
+    unsigned char acc[2][BM];
 };
 
 struct FusedParams {
@@ -85,7 +85,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
     const unsigned ntiles = (W + BM - 1) / BM;
     const unsigned half16 = lane >> 4;   // which of the warp's two walkers
     const unsigned ck = lane & 15;       // 16-byte chunk = columns 8*ck .. 8*ck+7
-    unsigned mma_phase = 0;
+    unsigned mma_phase = 0, tpar = 0;  // tpar: parity of the tile counter of this CTA
     long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
     unsigned long long target = p.bar_base;
 
@@ -116,9 +116,9 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                         step_draws<REPLAY>(p, h, i, j, z, u);
                         zz[t] = z;
                         if (ck == 0) {
-                            sm.z[r] = z;
-                            sm.u[r] = u;
-                            sm.j[r] = j;
+                            sm.z[tpar][r] = z;
+                            sm.u[tpar][r] = u;
+                            sm.j[tpar][r] = j;
                         }
                         const double *xk = p.x + (a0 + i) * d, *xj = p.x + (size_t)j * d;
 #pragma unroll
@@ -213,8 +213,8 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     const unsigned i = p.shard_begin + w;
                     const size_t k = a0 + i;
                     const double p1 = fp.lognorm - 0.5 * ss, p0 = p.lp[k];
-                    const bool acc = accept_exact<false>(p.nm1, sm.z[r], p1, p0, sm.u[r]);  // :260
-                    sm.acc[r] = acc ? 1 : 0;
+                    const bool acc = accept_exact<false>(p.nm1, sm.z[tpar][r], p1, p0, sm.u[tpar][r]);  // :260
+                    sm.acc[tpar][r] = acc ? 1 : 0;
                     if (acc) {
                         p.lp[k] = p1;
                         p.nacc[k] += 1u;
@@ -229,32 +229,56 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             mma_phase ^= 1;
             __syncthreads();
             // ------------------------------------------------ P3: accepted rows (and the chain)
+            // No barrier after P3: the next tile's P1 only writes sm.c (free since the MMA completed) and the
+            // OTHER parity of the per-row arrays; the bar.sync after that P1 orders everything else.
             for (unsigned r = warp * 2 + half16; r < BM; r += 2 * (kFusedThreads / 32)) {
                 const unsigned w = w0 + r;
                 if (w >= W) continue;
-                const bool acc = sm.acc[r] != 0;
-                if (!acc && !store) continue;
+                const bool accr = sm.acc[tpar][r] != 0;
+                if (!accr && !store) continue;
                 const unsigned i = p.shard_begin + w;
-                const double z = sm.z[r];
                 double *xk = p.x + (a0 + i) * d;
-                const double *xj = p.x + (size_t)sm.j[r] * d;
+                const double *xj = p.x + (size_t)sm.j[tpar][r] * d;
+                const double z = sm.z[tpar][r];
                 const size_t o = store ? chain_row(p, sidx, batch, i) : 0;
+                double2 xa[4], xb[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-#pragma unroll
-                    for (int q = 0; q < 2; ++q) {
-                        const int c = 2 * (ck + 16 * e) + q;
+                for (int e = 0; e < 4; ++e) {  // all loads of the row first
+                    const int c = 2 * (ck + 16 * e);
+                    xa[e] = make_double2(0.0, 0.0);
+                    xb[e] = make_double2(0.0, 0.0);
+                    if ((d & 1) == 0) {
                         if (c < d) {
-                            const double xo = xk[c];
-                            const double bj = __ldcg(xj + c);
-                            const double vv = acc ? dadd(bj, dmul(z, dsub(xo, bj))) : xo;  // :255, same bits
-                            if (acc) xk[c] = vv;                                        // :261
-                            if (store) __stcs(p.chain_x + o * d + c, vv);              // :268-272
+                            xa[e] = *reinterpret_cast<const double2 *>(xk + c);
+                            if (accr) xb[e] = __ldcg(reinterpret_cast<const double2 *>(xj + c));
+                        }
+                    } else {
+                        if (c < d) {
+                            xa[e].x = xk[c];
+                            if (accr) xb[e].x = __ldcg(xj + c);
+                        }
+                        if (c + 1 < d) {
+                            xa[e].y = xk[c + 1];
+                            if (accr) xb[e].y = __ldcg(xj + c + 1);
                         }
                     }
                 }
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int c = 2 * (ck + 16 * e);
+                    const double v0 = accr ? dadd(xb[e].x, dmul(z, dsub(xa[e].x, xb[e].x))) : xa[e].x;  // :255, same bits
+                    const double v1 = accr ? dadd(xb[e].y, dmul(z, dsub(xa[e].y, xb[e].y))) : xa[e].y;
+                    if (c < d) {
+                        if (accr) xk[c] = v0;                            // :261
+                        if (store) __stcs(p.chain_x + o * d + c, v0);   // :268-272
+                    }
+                    if (c + 1 < d) {
+                        if (accr) xk[c + 1] = v1;
+                        if (store) __stcs(p.chain_x + o * d + c + 1, v1);
+                    }
+                }
             }
-            __syncthreads();  // sm.c / sm.z / sm.acc are reused by the next tile
+            tpar ^= 1;
         }
         if (batch == 1) {
             if (store) ++sidx;

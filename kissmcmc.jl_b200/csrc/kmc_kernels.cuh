@@ -79,8 +79,14 @@ __device__ __forceinline__ void barrier_arrive(unsigned long long *ctr) {
 }
 __device__ __forceinline__ void barrier_wait(const unsigned long long *ctr, unsigned long long target) {
     unsigned long long v;
+    long long t0 = 0;
+    unsigned spins = 0;
     do {
         asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        if (v < target && (++spins & 0xFFFu) == 0) {  // watchdog (~20 s): a lost CTA must not hang the device
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 40000000000LL) __trap();
+        }
     } while (v < target);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
 }
