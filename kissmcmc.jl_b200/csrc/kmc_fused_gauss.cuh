@@ -5,7 +5,8 @@
 // between half-steps like emcee_run_kernel).  The matrix pieces A (3 x 32 KB bf16, SWIZZLE_128B)
 // are loaded once by TMA and stay in shared memory.  Per 128-walker tile:
 //
-//   P1  all 16 warps, 16 lanes per walker (two walkers in flight per half-warp), 8 columns per lane: draws (src/samplers.jl:250,:252,:260),
+//   P1  all 16 warps, 16 lanes per walker (two walkers in flight per half-warp), 8 columns per lane (the draws,
+//       src/samplers.jl:250,:252,:260, were made one thread per walker while the previous tile's GEMM ran):
 //       gather x_j (one contiguous 8d-byte row) and x_k, proposal y = xj + z(xk - xj) (:255) in FP64,
 //       centre, split into three bf16 pieces and store each 16-byte chunk DIRECTLY into the swizzled
 //       K-major UMMA tile in shared memory (chunk index XOR row%8 inside each 8 x 128 B atom) --
@@ -94,6 +95,20 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
         const bool store = (n > 0) && (phase == 0);  // :268
         const size_t a0 = batch ? (size_t)p.nhalf : 0;
 
+        // draws (src/samplers.jl:250,:252,:260) of one tile: one thread per walker row, into parity `par`
+        auto tile_draws = [&](unsigned tl, unsigned par, unsigned r) {
+            const unsigned w = tl * BM + r;
+            if (w < W) {
+                unsigned j;
+                double z, u;
+                step_draws<REPLAY>(p, h, p.shard_begin + w, j, z, u);
+                sm.z[par][r] = z;
+                sm.u[par][r] = u;
+                sm.j[par][r] = j;
+            }
+        };
+        if (blockIdx.x < ntiles && tid < BM) tile_draws(blockIdx.x, tpar, tid);
+        __syncthreads();
         for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const unsigned w0 = tile * BM;
             // ------------------------------------------------ P1: proposals -> swizzled bf16 pieces
@@ -111,15 +126,8 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     zz[t] = 0.0;
                     if (live[t]) {
                         const unsigned i = p.shard_begin + w;
-                        unsigned j;
-                        double z, u;
-                        step_draws<REPLAY>(p, h, i, j, z, u);
-                        zz[t] = z;
-                        if (ck == 0) {
-                            sm.z[tpar][r] = z;
-                            sm.u[tpar][r] = u;
-                            sm.j[tpar][r] = j;
-                        }
+                        const unsigned j = sm.j[tpar][r];
+                        zz[t] = sm.z[tpar][r];
                         const double *xk = p.x + (a0 + i) * d, *xj = p.x + (size_t)j * d;
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
@@ -225,6 +233,9 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     }
                     if (store) __stcs(p.chain_lp + chain_row(p, sidx, batch, i), acc ? p1 : p0);
                 }
+            }
+            else if (warp < 8) {  // idle during the GEMM: the NEXT tile's draws, into the other parity
+                if (tile + gridDim.x < ntiles) tile_draws(tile + gridDim.x, tpar ^ 1, (warp - 4) * 32 + lane);
             }
             mma_phase ^= 1;
             __syncthreads();
