@@ -36,23 +36,45 @@ def auto_window(taus, c) -> int:
     return len(taus) - 1
 
 
+def _mean_rho_torch(th):
+    """Chain-averaged normalised autocorrelation for every parameter on the GPU (batched FFT over
+    all chains and parameters at once): th [nchains, nsamples, ntheta] torch tensor -> [ntheta, nsamples//2]."""
+    import torch
+    x = th.to(torch.float64)
+    x = x - x.mean(dim=1, keepdim=True)
+    f = torch.fft.fft(x, dim=1)
+    acf = torch.fft.ifft(f * torch.conj(f), dim=1).real / (4 * x.shape[1])
+    acf = acf / acf[:, :1, :]
+    return acf[:, :x.shape[1] // 2, :].mean(dim=0).T.contiguous()
+
+
 def int_acorr(thetas, c=5, warn=True, warnat=50):
     """Integrated autocorrelation time per parameter, averaged over chains (:140-167).
 
-    thetas: [nchains, nsamples] or [nchains, nsamples, ntheta].
+    thetas: [nchains, nsamples] or [nchains, nsamples, ntheta]; a numpy array (host FFT, chain by
+    chain like the reference) or a torch tensor (one batched FFT on its device).
     Returns (tau[ntheta], converged[ntheta]); converged = nsamples / tau should be > ~50.
     If anything is NaN both are set to -1 (the reference's "hack")."""
     assert c > 1
-    th = np.asarray(thetas, dtype=np.float64)
-    if th.ndim == 2:
-        th = th[:, :, None]
-    nchains, nsamples, ntheta = th.shape
+    rho_dev = None
+    if type(thetas).__module__.startswith("torch"):      # device chains: one batched FFT on the GPU
+        tt = thetas if thetas.ndim == 3 else thetas[:, :, None]
+        nchains, nsamples, ntheta = tt.shape
+        rho_dev = _mean_rho_torch(tt).cpu().numpy()
+    else:
+        th = np.asarray(thetas, dtype=np.float64)
+        if th.ndim == 2:
+            th = th[:, :, None]
+        nchains, nsamples, ntheta = th.shape
     out = np.empty(ntheta)
     for n in range(ntheta):
-        rho = np.zeros(nsamples // 2)
-        for cc in range(nchains):
-            rho += acor1d(th[cc, :, n])
-        rho /= nchains
+        if rho_dev is not None:
+            rho = rho_dev[n]
+        else:
+            rho = np.zeros(nsamples // 2)
+            for cc in range(nchains):
+                rho += acor1d(th[cc, :, n])
+            rho /= nchains
         taus = 2 * np.cumsum(rho) - 1          # the -1: dfm/emcee issue 267
         window = auto_window(taus, c)
         out[n] = taus[window - 1]

@@ -85,3 +85,14 @@ def test_rhat_of_two_independent_gpu_ensembles(km):
         runs.append(th)
     rhat, neff, nthin = km.evaluate_convergence(*runs)
     assert np.all(rhat < 1.1) and neff > 1000
+
+
+def test_int_acorr_torch_path_matches_numpy(km):
+    import torch
+    x = np.stack([_ar1(0.5, 16, 3000, 3), _ar1(0.8, 16, 3000, 4)], axis=-1)
+    t0, c0 = km.int_acorr(x, warn=False)
+    t1, c1 = km.int_acorr(torch.from_numpy(x), warn=False)          # CPU tensor: same code path as CUDA tensors
+    np.testing.assert_allclose(t1, t0, rtol=1e-9)
+    if torch.cuda.is_available():
+        t2, _ = km.int_acorr(torch.from_numpy(x).cuda(), warn=False)
+        np.testing.assert_allclose(t2, t0, rtol=1e-9)
