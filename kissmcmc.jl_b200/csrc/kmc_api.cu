@@ -219,6 +219,7 @@ struct kmc_density_s {
     // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
     __nv_bfloat16 *d_Abf = nullptr;
     CUtensorMap mapA;
+    double *d_At = nullptr;  // FP64 kernel: A transposed and padded to 128 rows, [d][128]
 };
 
 namespace {
@@ -368,13 +369,14 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         return launch_gauss_tc(dn, sc, npts, out, st);
     }
     if (dn.ops.batch == 1) {
-        const int dp = d | 1;
-        const size_t smem = sizeof(double) * ((size_t)d * dp + 8 * (size_t)d);
+        const size_t smem = sizeof(double) * ((size_t)d * 128 + (size_t)(kmc::kWideThreads / 32) * d * kmc::kWidePts);
         cudaError_t e = cudaFuncSetAttribute(kmc::gaussian_wide_logp_kernel,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        const unsigned grid = (unsigned)std::min<long long>((npts + 7) / 8, 2 * 148);
-        kmc::gaussian_wide_logp_kernel<<<grid, 256, smem, st>>>(X, out, npts, d, dn.d_params);
+        const long long ngroups = (npts + kmc::kWidePts - 1) / kmc::kWidePts;
+        const int wpb = kmc::kWideThreads / 32;
+        const unsigned grid = (unsigned)std::min<long long>((ngroups + wpb - 1) / wpb, dn.nsm);
+        kmc::gaussian_wide_logp_kernel<<<grid, kmc::kWideThreads, smem, st>>>(X, out, npts, d, dn.d_params, dn.d_At);
         return cudaGetLastError();
     }
     if (dn.ops.batch == 2 && dn.tc_ok && dn.tc_on) {  // tcgen05 logits GEMM + fused softplus row sums
@@ -509,6 +511,13 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
         if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && ops.batch == 1) {  // A^T padded to 128 rows for the FP64 kernel
+            std::vector<double> At((size_t)d * 128, 0.0);
+            for (int i = 0; i < d; ++i)
+                for (int j = 0; j < d; ++j) At[(size_t)j * 128 + i] = params[d + (size_t)i * d + j];
+            e = dev_alloc(&h->d_At, sizeof(double) * At.size(), device);
+            if (e == cudaSuccess) e = cudaMemcpy(h->d_At, At.data(), sizeof(double) * At.size(), cudaMemcpyHostToDevice);
+        }
         if (e == cudaSuccess && ops.batch == 1) {  // matrix pieces for the tcgen05 Mahalanobis GEMM
             int nsm = 0;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
@@ -606,6 +615,7 @@ int32_t kmc_density_destroy(kmc_density_t h) {
     dev_free(h->d_Xbf);
     dev_free(h->d_xty);
     dev_free(h->d_Abf);
+    dev_free(h->d_At);
     delete h;
     return KMC_OK;
 }
@@ -685,6 +695,9 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     if (nwalkers / 2 >= (1LL << 32)) return fail(KMC_ERR_INVALID, "too many walkers");
     if (opts->mode != KMC_MODE_PHILOX && opts->mode != KMC_MODE_REPLAY)
         return fail(KMC_ERR_INVALID, "unknown mode %d", opts->mode);
+    if (density->ops.batch && opts->device != density->device)
+        return fail(KMC_ERR_INVALID, "the density's parameters / data live on device %d, the sampler was asked for device %d",
+                    density->device, opts->device);
 
     CU_TRY(cudaSetDevice(opts->device));
     auto *s = new kmc_sampler_s;

@@ -158,45 +158,66 @@ __global__ void __launch_bounds__(256) accept_recompute_kernel(const RunParams p
 }
 
 // ------------------------------------------------------------------ dense Gaussian, FP64
-// params (device): mu[d], A[d][d] row-major, lognorm.  One warp per point; lane l owns rows
-// l, l+32, l+64, l+96 of y = A (x - mu); A is staged transposed in shared memory (At[j][i],
-// conflict-free), the centred point per warp in shared memory (broadcast reads).
+// params (device): mu[d], A[d][d] row-major, lognorm.  A is staged transposed in shared memory
+// (At[j][i], conflict-free), the centred points per warp in shared memory (broadcast reads).
 // logp = lognorm - 0.5 * sum_i y_i^2;  FMA accumulation, warp-tree reduction: agrees with the
 // oracle's sequential order to ~1e-14 relative (tolerance stated in the tests: 1e-12).
 constexpr int kWideMaxD = 128;
+constexpr int kWideThreads = 512;  // 16 warps
+constexpr int kWidePts = 4;        // points per warp per pass (register tile: 4 points x 4 rows per lane)
 
-__global__ void __launch_bounds__(256) gaussian_wide_logp_kernel(const double *__restrict__ X, double *__restrict__ out,
-                                                                 long long npts, int d, const double *__restrict__ prm) {
+// Register-tiled: a warp processes 4 points at once, lane l owns rows l, l+32, l+64, l+96 of y for each
+// of them (16 FP64 accumulators), so every A element read from shared memory feeds 4 FMAs and every
+// centred coordinate (broadcast 32-byte read of the 4 points) feeds 4 FMAs: 16 DFMA per 6 LDS -- the
+// FP64 pipe, not the LSU, is the bound.  At is padded to 128 rows of zeros (no masks in the loop).
+// Accumulation order per (point, row) is j = 0..d-1 with FMA, then rows in order, then the xor tree.
+__global__ void __launch_bounds__(kWideThreads, 1) gaussian_wide_logp_kernel(const double *__restrict__ X,
+                                                                              double *__restrict__ out, long long npts,
+                                                                              int d, const double *__restrict__ prm,
+                                                                              const double *__restrict__ At_g) {
     extern __shared__ double sm[];
-    const int dp = d | 1;  // odd row pitch: conflict-free transposed reads
-    double *At = sm;                     // [d][dp]  At[j*dp + i] = A[i][j]
-    double *cb = sm + (size_t)d * dp;    // [warps][d]
+    double *At = sm;                          // [d][128]  At[j*128 + i] = A[i][j], zero for i >= d (At_g: same, in global)
+    double *cb = sm + (size_t)d * 128;        // [warps][d][kWidePts]
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-    for (int e = threadIdx.x; e < d * d; e += blockDim.x) {
-        const int i = e / d, j = e % d;
-        At[j * dp + i] = prm[d + e];
-    }
+    for (int e = threadIdx.x * 2; e < d * 128; e += blockDim.x * 2)  // coalesced 16-byte copies of the pre-transposed matrix
+        *reinterpret_cast<double2 *>(At + e) = *reinterpret_cast<const double2 *>(At_g + e);
     __syncthreads();
     const double lognorm = prm[d + (size_t)d * d];
-    double *c = cb + (size_t)wib * d;
-    for (long long pt = (long long)blockIdx.x * nwarp + wib; pt < npts; pt += (long long)gridDim.x * nwarp) {
-        const double *x = X + pt * d;
-        for (int j = lane; j < d; j += 32) c[j] = x[j] - prm[j];
-        __syncwarp();
-        double acc[4] = {0.0, 0.0, 0.0, 0.0};
-        for (int j = 0; j < d; ++j) {
-            const double cj = c[j];
-            const double *row = At + j * dp + lane;
+    double *c = cb + (size_t)wib * d * kWidePts;
+    const long long ngroups = (npts + kWidePts - 1) / kWidePts;
+    for (long long g = (long long)blockIdx.x * nwarp + wib; g < ngroups; g += (long long)gridDim.x * nwarp) {
+        const long long pt0 = g * kWidePts;
 #pragma unroll
-            for (int r = 0; r < 4; ++r)
-                if (lane + 32 * r < d) acc[r] = fma(row[32 * r], cj, acc[r]);
+        for (int w = 0; w < kWidePts; ++w) {
+            const long long pt = pt0 + w;
+            for (int j = lane; j < d; j += 32) c[j * kWidePts + w] = pt < npts ? X[pt * d + j] - prm[j] : 0.0;
         }
-        double ss = 0.0;
+        __syncwarp();
+        double acc[kWidePts][4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r)
-            if (lane + 32 * r < d) ss = fma(acc[r], acc[r], ss);
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        if (lane == 0) out[pt] = lognorm - 0.5 * ss;
+        for (int w = 0; w < kWidePts; ++w)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) acc[w][r] = 0.0;
+        for (int j = 0; j < d; ++j) {
+            const double2 c01 = *reinterpret_cast<const double2 *>(c + j * kWidePts);
+            const double2 c23 = *reinterpret_cast<const double2 *>(c + j * kWidePts + 2);
+            const double cj[4] = {c01.x, c01.y, c23.x, c23.y};
+            const double *row = At + j * 128 + lane;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const double a = row[32 * r];
+#pragma unroll
+                for (int w = 0; w < kWidePts; ++w) acc[w][r] = fma(a, cj[w], acc[w][r]);
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < kWidePts; ++w) {
+            double ss = 0.0;
+#pragma unroll
+            for (int r = 0; r < 4; ++r) ss = fma(acc[w][r], acc[w][r], ss);
+            for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            if (lane == 0 && pt0 + w < npts) out[pt0 + w] = lognorm - 0.5 * ss;
+        }
         __syncwarp();
     }
 }
