@@ -414,7 +414,7 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsig
 }
 
 template <template <int> class Dn, int D, bool PEER>
-__global__ void __launch_bounds__(kBulkThreads, 2) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
+__global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
     static_assert(D % 2 == 0, "rows must be multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     constexpr unsigned T = kBulkThreads, ROWB = D * 8;
