@@ -288,3 +288,25 @@ def test_large_ensemble_general_kernels(km, orc):
     od = orc.Density("gaussian", 10, prm)
     sub = slice(0, None, 997)
     assert np.array_equal(od.eval(a["x"][sub]), a["lp"][sub])
+
+
+def test_rosenbrock_analytic_moments_at_scale(km):
+    """Free-running check against the ANALYTIC posterior of the reference's Rosenbrock/20 test density
+    (test/runtests.jl:68): y|x ~ N(x^2, 0.1), x ~ N(1, 10)  =>  E = [1, 11], std = [sqrt(10), sqrt(240.1)].
+    (The reference quotes [0.98, 10.3] / [3.1, 13.8] from its own 10^9-step run, test/runtests.jl:70-72, and
+    tests within 0.6*std of those.)  9.8e8 walker-steps, moments reduced on the device; the tails mix
+    slowly (acceptance 0.22), hence the 3-4 % bands."""
+    ld = km.rosenbrock()
+    nw, nitw = 1 << 14, 60000
+    x0 = km.make_theta0s(np.array([0.0, 0.0]), 0.1, ld, nw, seed=1)
+    s = km.Sampler(ld, x0, nitw, nitw // 3, 50, 2.0, seed=11)
+    s.run(-1)
+    mean, var, n = s.chain_moments()
+    s.close()
+    std = np.sqrt(var)
+    assert n == nw * ((nitw - nitw // 3) // 50)
+    assert abs(mean[0] - 1.0) < 0.1 and abs(std[0] - 10 ** 0.5) < 0.12
+    assert abs(mean[1] - 11.0) < 0.7 and abs(std[1] - 240.1 ** 0.5) < 0.9
+    # and inside the reference's own acceptance band around its quoted values
+    assert np.all(np.abs(mean - [0.98, 10.3]) < 0.6 * np.array([3.1, 13.8]))
+    assert np.all(np.abs(std - [3.1, 13.8]) < 0.6 * np.array([3.1, 13.8]))
