@@ -700,6 +700,13 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
                     density->device, opts->device);
 
     CU_TRY(cudaSetDevice(opts->device));
+    if (const char *g = getenv("KMC_L2_FETCH")) {  // experiment: L2 fetch granularity (bytes) for random row gathers
+        size_t before = 0, after = 0;
+        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "KMC_L2_FETCH: %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
+    }
     auto *s = new kmc_sampler_s;
     s->dn = density;
     s->opts = *opts;

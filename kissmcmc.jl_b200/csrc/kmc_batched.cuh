@@ -105,15 +105,14 @@ __global__ void __launch_bounds__(256) propose_pieces_kernel(const RunParams p, 
     step_draws<REPLAY>(p, h, i, j, z, u);
     const double *xk = p.x + ((size_t)(batch ? p.nhalf : 0u) + i) * d;
     const double *xj = p.x + (size_t)j * d;
-    for (int c = lane; c < 128; c += 32) {
-        double v = 0.0;
-        if (c < d) v = dadd(xj[c], dmul(z, dsub(xk[c], xj[c]))) - mu[c];  // :255, centred
+    for (int c = 2 * lane; c < 128; c += 64) {  // column pairs: one 4-byte store per piece
+        double v0 = 0.0, v1 = 0.0;
+        if (c < d) v0 = dadd(xj[c], dmul(z, dsub(xk[c], xj[c]))) - mu[c];  // :255, centred
+        if (c + 1 < d) v1 = dadd(xj[c + 1], dmul(z, dsub(xk[c + 1], xj[c + 1]))) - mu[c + 1];
+        unsigned pk[3];
+        split3_pair(v0, v1, pk);
 #pragma unroll
-        for (int pc = 0; pc < 3; ++pc) {
-            const __nv_bfloat16 hb = __double2bfloat16(v);
-            row[pc * plane + c] = hb;
-            v -= (double)__bfloat162float(hb);
-        }
+        for (int pc = 0; pc < 3; ++pc) *reinterpret_cast<unsigned *>(row + pc * plane + c) = pk[pc];
     }
     if (lane == 0) {
         b.z[w] = z;

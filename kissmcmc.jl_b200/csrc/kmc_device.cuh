@@ -15,6 +15,30 @@ __device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a,
 __device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double ddiv(double a, double b) { return __ddiv_rn(a, b); }
 
+// ------------------------------------------------------------------ FP64 -> three bf16 pieces (tcgen05 operands)
+// Walker coordinates for the tensor-core log-densities: v is rounded ONCE to FP32 (24 significant
+// bits) and that value is split exactly: h0 = RN_bf16(f), r1 = f - h0, h1 = RN_bf16(r1),
+// r2 = r1 - h1, h2 = RN_bf16(r2) = r2.  Both subtractions are exact in FP32 (the residual of
+// rounding a 24-bit number to 8 bits has at most 16 significant bits, then 8), so
+// h0 + h1 + h2 == RN_f32(v).  Two coordinates at a time: one F2F.F32.F64 each, then per piece one
+// packed F2FP.BF16 + two integer unpacks + two FSUB -- a direct FP64 split costs four XU-pipe
+// F2F conversions per coordinate and piece and was the bound of the fused kernel's proposal phase.
+// pk[pc] = bf16(v0 piece) | bf16(v1 piece) << 16.  Every kernel that feeds points to a tcgen05
+// Gaussian GEMM uses this one function, so their operands agree bit for bit.
+__device__ __forceinline__ void split3_pair(double v0, double v1, unsigned (&pk)[3]) {
+    float f0 = __double2float_rn(v0), f1 = __double2float_rn(v1);
+#pragma unroll
+    for (int pc = 0; pc < 3; ++pc) {
+        unsigned u;
+        asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(f1), "f"(f0));  // upper half <- f1, lower half <- f0
+        pk[pc] = u;
+        if (pc < 2) {
+            f0 = __fsub_rn(f0, __uint_as_float(u << 16));
+            f1 = __fsub_rn(f1, __uint_as_float(u & 0xFFFF0000u));
+        }
+    }
+}
+
 // ------------------------------------------------------------------ Philox4x32-10
 struct Philox4 {
     uint32_t r0, r1, r2, r3;

@@ -28,6 +28,10 @@ namespace kmc {
 namespace tc {
 
 constexpr int kFusedThreads = 512;
+#ifndef KMC_K2F_P3FLIGHT
+#define KMC_K2F_P3FLIGHT 1
+#endif
+constexpr int kP3Flight = KMC_K2F_P3FLIGHT;  // listed rows per half-warp in flight in P3
 
 struct __align__(1024) FusedSmem {
     unsigned char a[PIECES][GPIECE_BYTES];  // matrix pieces (B operand), resident
@@ -36,6 +40,9 @@ struct __align__(1024) FusedSmem {
     unsigned tmem_base;
     double z[2][BM], u[2][BM];   // per-row draws, double-buffered by tile parity (P3 of tile t overlaps P1 of tile t+1)
     unsigned j[2][BM];
+    float q[2][BM];              // FP32 accept-filter term of the draw (filter_q), NaN = exact path
+    unsigned nlist[2];           // rows of the tile that P3 has to touch (accepted, or all when the iteration is stored)
+    unsigned char list[2][BM];
     unsigned char acc[2][BM];
 };
 
@@ -47,6 +54,12 @@ struct FusedParams {
 
 // byte offset of the 16-byte chunk (row r, chunk index ck in 0..15 = 8 bf16 columns each) inside a
 // piece stored as [2 k-halves][128 rows][128 B] with the 128-byte swizzle
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 __device__ __forceinline__ unsigned sw128_chunk_offset(unsigned r, unsigned ck) {
     const unsigned kh = ck >> 3, c8 = ck & 7;
     return kh * (GPIECE_BYTES / 2) + (r >> 3) * 1024 + (r & 7) * 128 + ((c8 ^ (r & 7)) << 4);
@@ -57,10 +70,12 @@ __global__ void __launch_bounds__(kFusedThreads, 1)
 gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams p, const FusedParams fp) {
     extern __shared__ unsigned char smem_raw[];
     FusedSmem &sm = *reinterpret_cast<FusedSmem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = tid >> 5;
     const int d = fp.d;
 
     if (tid == 0) {
+        sm.nlist[0] = sm.nlist[1] = 0u;
         mbar_init(&sm.afull, 1);
         mbar_init(&sm.mma_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -73,7 +88,9 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tmem = sm.tmem_base;
+    // lane-0 shuffle: tells ptxas the TMEM base is warp-uniform, so the MMA issue loop keeps it in a uniform register
+    // instead of an ELECT + R2UR waterfall per tcgen05.mma (the issue stream, not the tensor pipe, was the bound)
+    const unsigned tmem = __shfl_sync(0xffffffffu, sm.tmem_base, 0);
     if (tid == 0) {  // the matrix: once per CTA
         mbar_expect_tx(&sm.afull, PIECES * GPIECE_BYTES);
         for (int pc = 0; pc < PIECES; ++pc)
@@ -82,13 +99,26 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
     }
     mbar_wait(&sm.afull, 0);
 
+    // Tiles are balanced over the grid: every CTA gets the same number of tiles per half-step and a tile holds
+    // tr <= 128 walkers (2^15 active walkers on 148 CTAs: 296 tiles of 111 rows instead of 256 of 128, of which 40
+    // CTAs would get one and 108 two).  A row of the GEMM depends on its own walker only, so the tiling changes no bit.
     const unsigned W = p.shard_end - p.shard_begin;
-    const unsigned ntiles = (W + BM - 1) / BM;
+    const unsigned waves = ((W + BM - 1) / BM + gridDim.x - 1) / gridDim.x;
+    const unsigned tr = min((unsigned)BM, (W + waves * gridDim.x - 1) / (waves * gridDim.x));  // walkers per tile
+    const unsigned trh = (tr + 1) / 2;
+    const unsigned ntiles = (W + tr - 1) / tr;
+    const int nk = (d + 15) / 16;        // k-steps (and 16-column groups of the output) that hold data
     const unsigned half16 = lane >> 4;   // which of the warp's two walkers
     const unsigned ck = lane & 15;       // 16-byte chunk = columns 8*ck .. 8*ck+7
     unsigned mma_phase = 0, tpar = 0;  // tpar: parity of the tile counter of this CTA
     long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
     unsigned long long target = p.bar_base;
+#ifdef KMC_K2F_PROF
+    long long pt[6] = {0, 0, 0, 0, 0, 0}, pc0 = clock64();
+#define K2F_TICK(i) do { const long long c_ = clock64(); pt[i] += c_ - pc0; pc0 = c_; } while (0)
+#else
+#define K2F_TICK(i) do { } while (0)
+#endif
 
     for (long long h = p.h0; h < p.h1; ++h) {
         const unsigned batch = (unsigned)(h & 1);
@@ -97,32 +127,34 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
 
         // draws (src/samplers.jl:250,:252,:260) of one tile: one thread per walker row, into parity `par`
         auto tile_draws = [&](unsigned tl, unsigned par, unsigned r) {
-            const unsigned w = tl * BM + r;
-            if (w < W) {
+            const unsigned w = tl * tr + r;
+            if (r < tr && w < W) {
                 unsigned j;
                 double z, u;
                 step_draws<REPLAY>(p, h, p.shard_begin + w, j, z, u);
                 sm.z[par][r] = z;
                 sm.u[par][r] = u;
                 sm.j[par][r] = j;
+                sm.q[par][r] = filter_q<REPLAY>(p, z, u);
             }
         };
         if (blockIdx.x < ntiles && tid < BM) tile_draws(blockIdx.x, tpar, tid);
         __syncthreads();
+        K2F_TICK(0);
         for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const unsigned w0 = tile * BM;
+            const unsigned w0 = tile * tr;
             // ------------------------------------------------ P1: proposals -> swizzled bf16 pieces
             // lane handles column pairs cp = ck + 16 e (columns 2cp, 2cp+1), e = 0..3: every load instruction of
             // a half-warp reads 256 contiguous bytes of the row
             // Two rows per half-warp are in flight at once (rows r and r + 64): all loads first, then the math.
-            for (unsigned rb = warp * 2 + half16; rb < BM / 2; rb += 2 * (kFusedThreads / 32)) {
+            for (unsigned rb = warp * 2 + half16; rb < trh; rb += 2 * (kFusedThreads / 32)) {
                 double2 xa[2][4], xb[2][4];
                 double zz[2];
                 bool live[2];
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const unsigned r = rb + t * (BM / 2), w = w0 + r;
-                    live[t] = w < W;
+                    const unsigned r = rb + t * trh, w = w0 + r;
+                    live[t] = r < tr && w < W;
                     zz[t] = 0.0;
                     if (live[t]) {
                         const unsigned i = p.shard_begin + w;
@@ -154,34 +186,39 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                 }
 #pragma unroll
                 for (int t = 0; t < 2; ++t) {
-                    const unsigned r = rb + t * (BM / 2);
+                    if (!live[t]) continue;  // rows past the tile: whatever the buffer holds only reaches accumulator rows nobody reads
+                    const unsigned r = rb + t * trh;
                     double v[8];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 2 * (ck + 16 * e);
-                        v[2 * e] = (live[t] && c < d) ? dadd(xb[t][e].x, dmul(zz[t], dsub(xa[t][e].x, xb[t][e].x))) - fp.mu[c] : 0.0;  // :255, centred
-                        v[2 * e + 1] = (live[t] && c + 1 < d) ? dadd(xb[t][e].y, dmul(zz[t], dsub(xa[t][e].y, xb[t][e].y))) - fp.mu[c + 1] : 0.0;
+                        v[2 * e] = (c < d) ? dadd(xb[t][e].x, dmul(zz[t], dsub(xa[t][e].x, xb[t][e].x))) - fp.mu[c] : 0.0;  // :255, centred
+                        v[2 * e + 1] = (c + 1 < d) ? dadd(xb[t][e].y, dmul(zz[t], dsub(xa[t][e].y, xb[t][e].y))) - fp.mu[c + 1] : 0.0;
                     }
 #pragma unroll
-                    for (int pc = 0; pc < PIECES; ++pc) {
+                    for (int e = 0; e < 4; ++e) {
+                        unsigned pk[PIECES];
+                        split3_pair(v[2 * e], v[2 * e + 1], pk);
+                        const unsigned cp = ck + 16 * e;  // column pair -> 4 bytes inside chunk cp/4
+                        const unsigned off = sw128_chunk_offset(r, cp >> 2) + ((cp & 3) << 2);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const __nv_bfloat16 h0 = __double2bfloat16(v[2 * e]), h1 = __double2bfloat16(v[2 * e + 1]);
-                            v[2 * e] -= (double)__bfloat162float(h0);
-                            v[2 * e + 1] -= (double)__bfloat162float(h1);
-                            const unsigned cp = ck + 16 * e;  // column pair -> 4 bytes inside chunk cp/4
-                            *reinterpret_cast<unsigned *>(sm.c[pc] + sw128_chunk_offset(r, cp >> 2) + ((cp & 3) << 2)) =
-                                (unsigned)__bfloat16_as_ushort(h0) | ((unsigned)__bfloat16_as_ushort(h1) << 16);
-                        }
+                        for (int pc = 0; pc < PIECES; ++pc) *reinterpret_cast<unsigned *>(sm.c[pc] + off) = pk[pc];
                     }
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> tensor-core proxy
             __syncthreads();
+            K2F_TICK(1);
             // ------------------------------------------------ P2: tcgen05 GEMM, epilogue, accept
+#ifdef KMC_K2F_ELECT
+            if (warp == 0 && elect_one()) {
+#else
             if (tid == 0) {
+#endif
                 tc_fence_after();
-                constexpr unsigned idesc = idesc_bf16_f32(BM, GN);
+                // only the first ceil(d/16) k-steps and ceil(d/16)*16 output columns: the rest are zero padding
+                // (adding +0 products changes no bit, so this equals the full 128x128x128 product)
+                const unsigned idesc = idesc_bf16_f32(BM, nk * 16);
                 const int pc_c[6] = {2, 0, 1, 1, 0, 0};
                 const int pc_a[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
@@ -189,6 +226,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     const unsigned cb = smem_u32(sm.c[pc_c[pr]]), ab = smem_u32(sm.a[pc_a[pr]]);
 #pragma unroll
                     for (int k = 0; k < GK / 16; ++k) {
+                        if (k >= nk) break;
                         const unsigned off = (k >> 2) * (GPIECE_BYTES / 2) + (k & 3) * 32;
                         tc_mma(tmem, smem_desc_sw128(cb + off), smem_desc_sw128(ab + off), idesc, (pr | k) ? 1u : 0u);
                     }
@@ -197,6 +235,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             }
             if (warp < 4) {
                 mbar_wait(&sm.mma_done, mma_phase);
+                K2F_TICK(5);
                 __syncwarp();  // lane 0 came here from the MMA issue: converge before the .aligned TMEM loads
                 tc_fence_after();
                 const int r = warp * 32 + lane;
@@ -210,19 +249,26 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     float part = 0.0f;
 #pragma unroll
                     for (int e = 0; e < 32; ++e) {
-                        const float y = __uint_as_float(v[e]);
+                        const float y = cb + e < nk * 16 ? __uint_as_float(v[e]) : 0.0f;  // columns past the MMA's N are stale
                         part = fmaf(y, y, part);
                     }
                     ss += (double)part;
                 }
                 tc_fence_before();
                 const unsigned w = w0 + r;
-                if (w < W) {
+                if ((unsigned)r < tr && w < W) {
                     const unsigned i = p.shard_begin + w;
                     const size_t k = a0 + i;
                     const double p1 = fp.lognorm - 0.5 * ss, p0 = p.lp[k];
-                    const bool acc = accept_exact<false>(p.nm1, sm.z[tpar][r], p1, p0, sm.u[tpar][r]);  // :260
+                    // :260 -- the FP32 filter of kmc_kernels.cuh decides exactly like the FP64 expression whenever
+                    // |tt| is above its rigorous margin; everything else takes the FP64 expression itself
+                    const double tt = (p1 - p0) + (double)sm.q[tpar][r] * 0.6931471805599453;
+                    bool acc;
+                    if (tt > (double)p.margin) acc = true;
+                    else if (tt < -(double)p.margin) acc = false;
+                    else acc = accept_exact<false>(p.nm1, sm.z[tpar][r], p1, p0, sm.u[tpar][r]);
                     sm.acc[tpar][r] = acc ? 1 : 0;
+                    if (acc || store) sm.list[tpar][atomicAdd(&sm.nlist[tpar], 1u)] = (unsigned char)r;
                     if (acc) {
                         p.lp[k] = p1;
                         p.nacc[k] += 1u;
@@ -236,60 +282,84 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             }
             else if (warp < 8) {  // idle during the GEMM: the NEXT tile's draws, into the other parity
                 if (tile + gridDim.x < ntiles) tile_draws(tile + gridDim.x, tpar ^ 1, (warp - 4) * 32 + lane);
+            } else if (tid == 8 * 32) {
+                sm.nlist[tpar ^ 1] = 0u;  // the previous tile's P3 finished before the barrier that closed this tile's P1
             }
             mma_phase ^= 1;
             __syncthreads();
+            K2F_TICK(2);
             // ------------------------------------------------ P3: accepted rows (and the chain)
             // No barrier after P3: the next tile's P1 only writes sm.c (free since the MMA completed) and the
             // OTHER parity of the per-row arrays; the bar.sync after that P1 orders everything else.
-            for (unsigned r = warp * 2 + half16; r < BM; r += 2 * (kFusedThreads / 32)) {
-                const unsigned w = w0 + r;
-                if (w >= W) continue;
-                const bool accr = sm.acc[tpar][r] != 0;
-                if (!accr && !store) continue;
-                const unsigned i = p.shard_begin + w;
-                double *xk = p.x + (a0 + i) * d;
-                const double *xj = p.x + (size_t)sm.j[tpar][r] * d;
-                const double z = sm.z[tpar][r];
-                const size_t o = store ? chain_row(p, sidx, batch, i) : 0;
-                double2 xa[4], xb[4];
+            // Two listed rows per half-warp in flight (all loads first, then the math and the stores).
+            const unsigned nl = sm.nlist[tpar];
+            for (unsigned l0 = warp * 2 + half16; l0 < nl; l0 += kP3Flight * 2 * (kFusedThreads / 32)) {
+                double2 xa[kP3Flight][4], xb[kP3Flight][4];
+                unsigned rr[kP3Flight];
+                bool live[kP3Flight], accr[kP3Flight];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {  // all loads of the row first
-                    const int c = 2 * (ck + 16 * e);
-                    xa[e] = make_double2(0.0, 0.0);
-                    xb[e] = make_double2(0.0, 0.0);
-                    if ((d & 1) == 0) {
-                        if (c < d) {
-                            xa[e] = *reinterpret_cast<const double2 *>(xk + c);
-                            if (accr) xb[e] = __ldcg(reinterpret_cast<const double2 *>(xj + c));
-                        }
-                    } else {
-                        if (c < d) {
-                            xa[e].x = xk[c];
-                            if (accr) xb[e].x = __ldcg(xj + c);
-                        }
-                        if (c + 1 < d) {
-                            xa[e].y = xk[c + 1];
-                            if (accr) xb[e].y = __ldcg(xj + c + 1);
+                for (int t = 0; t < kP3Flight; ++t) {
+                    const unsigned l = l0 + t * 2 * (kFusedThreads / 32);
+                    live[t] = l < nl;
+                    rr[t] = live[t] ? sm.list[tpar][l] : 0u;
+                    accr[t] = live[t] && sm.acc[tpar][rr[t]] != 0;
+                    if (!live[t]) continue;
+                    const double *xk = p.x + (a0 + p.shard_begin + w0 + rr[t]) * d;
+                    const double *xj = p.x + (size_t)sm.j[tpar][rr[t]] * d;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 2 * (ck + 16 * e);
+                        xa[t][e] = make_double2(0.0, 0.0);
+                        xb[t][e] = make_double2(0.0, 0.0);
+                        if ((d & 1) == 0) {
+                            if (c < d) {
+                                xa[t][e] = *reinterpret_cast<const double2 *>(xk + c);
+                                if (accr[t]) xb[t][e] = __ldcg(reinterpret_cast<const double2 *>(xj + c));
+                            }
+                        } else {
+                            if (c < d) {
+                                xa[t][e].x = xk[c];
+                                if (accr[t]) xb[t][e].x = __ldcg(xj + c);
+                            }
+                            if (c + 1 < d) {
+                                xa[t][e].y = xk[c + 1];
+                                if (accr[t]) xb[t][e].y = __ldcg(xj + c + 1);
+                            }
                         }
                     }
                 }
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int c = 2 * (ck + 16 * e);
-                    const double v0 = accr ? dadd(xb[e].x, dmul(z, dsub(xa[e].x, xb[e].x))) : xa[e].x;  // :255, same bits
-                    const double v1 = accr ? dadd(xb[e].y, dmul(z, dsub(xa[e].y, xb[e].y))) : xa[e].y;
-                    if (c < d) {
-                        if (accr) xk[c] = v0;                            // :261
-                        if (store) __stcs(p.chain_x + o * d + c, v0);   // :268-272
-                    }
-                    if (c + 1 < d) {
-                        if (accr) xk[c + 1] = v1;
-                        if (store) __stcs(p.chain_x + o * d + c + 1, v1);
+                for (int t = 0; t < kP3Flight; ++t) {
+                    if (!live[t]) continue;
+                    const unsigned i = p.shard_begin + w0 + rr[t];
+                    double *xk = p.x + (a0 + i) * d;
+                    const double z = sm.z[tpar][rr[t]];
+                    const size_t o = store ? chain_row(p, sidx, batch, i) : 0;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int c = 2 * (ck + 16 * e);
+                        const double v0 = accr[t] ? dadd(xb[t][e].x, dmul(z, dsub(xa[t][e].x, xb[t][e].x))) : xa[t][e].x;  // :255, same bits
+                        const double v1 = accr[t] ? dadd(xb[t][e].y, dmul(z, dsub(xa[t][e].y, xb[t][e].y))) : xa[t][e].y;
+                        if ((d & 1) == 0) {  // even d: rows are 16-byte aligned, one 16-byte store per column pair
+                            if (c < d) {
+                                if (accr[t]) *reinterpret_cast<double2 *>(xk + c) = make_double2(v0, v1);                  // :261
+                                if (store) __stcs(reinterpret_cast<double2 *>(p.chain_x + o * d + c), make_double2(v0, v1));  // :268-272
+                            }
+                        } else {
+                            if (c < d) {
+                                if (accr[t]) xk[c] = v0;
+                                if (store) __stcs(p.chain_x + o * d + c, v0);
+                            }
+                            if (c + 1 < d) {
+                                if (accr[t]) xk[c + 1] = v1;
+                                if (store) __stcs(p.chain_x + o * d + c + 1, v1);
+                            }
+                        }
                     }
                 }
             }
             tpar ^= 1;
+            K2F_TICK(3);
         }
         if (batch == 1) {
             if (store) ++sidx;
@@ -307,7 +377,13 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                 __syncthreads();
             }
         }
+        K2F_TICK(4);
     }
+#ifdef KMC_K2F_PROF
+    if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+        printf("K2F cta %d cycles: draws %lld P1 %lld mma %lld epilogue %lld P3 %lld barrier %lld (half-steps %lld)\n", (int)blockIdx.x,
+               pt[0], pt[1], pt[5], pt[2], pt[3], pt[4], (long long)(p.h1 - p.h0));
+#endif
 
     tc_fence_before();
     __syncthreads();

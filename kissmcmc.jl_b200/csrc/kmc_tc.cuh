@@ -30,6 +30,8 @@
 
 #include <cstdint>
 
+#include "kmc_device.cuh"
+
 namespace kmc {
 namespace tc {
 
@@ -539,8 +541,15 @@ __global__ void split_rows128_kernel(const double *__restrict__ X, const double 
     const long long r = e / GK;
     const int c = (int)(e % GK);
     double v = (r < rows && c < d) ? X[r * d + c] - (mu ? mu[c] : 0.0) : 0.0;
+    if (mu) {  // points: the split every proposal kernel uses (kmc_device.cuh), so all paths agree bit for bit
+        unsigned pk[3];
+        split3_pair(v, 0.0, pk);
 #pragma unroll
-    for (int pc = 0; pc < PIECES; ++pc) {
+        for (int pc = 0; pc < PIECES; ++pc) out[(size_t)pc * rpad * GK + e] = __ushort_as_bfloat16((unsigned short)pk[pc]);
+        return;
+    }
+#pragma unroll
+    for (int pc = 0; pc < PIECES; ++pc) {  // the matrix (once per density): round-to-nearest pieces of the FP64 value
         const __nv_bfloat16 h = __double2bfloat16(v);
         out[(size_t)pc * rpad * GK + e] = h;
         v -= (double)__bfloat162float(h);
