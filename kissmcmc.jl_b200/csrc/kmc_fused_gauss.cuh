@@ -40,6 +40,7 @@ struct __align__(1024) FusedSmem {
     unsigned tmem_base;
     double z[2][BM], u[2][BM];   // per-row draws, double-buffered by tile parity (P3 of tile t overlaps P1 of tile t+1)
     unsigned j[2][BM];
+    alignas(16) double mu[GK];   // the mean, zero-padded to 128 columns (read as double2)
     float q[2][BM];              // FP32 accept-filter term of the draw (filter_q), NaN = exact path
     unsigned nlist[2];           // rows of the tile that P3 has to touch (accepted, or all when the iteration is stored)
     unsigned char list[2][BM];
@@ -74,6 +75,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
     const int warp = tid >> 5;
     const int d = fp.d;
 
+    if (tid < GK) sm.mu[tid] = tid < d ? fp.mu[tid] : 0.0;
     if (tid == 0) {
         sm.nlist[0] = sm.nlist[1] = 0u;
         mbar_init(&sm.afull, 1);
@@ -105,7 +107,6 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
     const unsigned W = p.shard_end - p.shard_begin;
     const unsigned waves = ((W + BM - 1) / BM + gridDim.x - 1) / gridDim.x;
     const unsigned tr = min((unsigned)BM, (W + waves * gridDim.x - 1) / (waves * gridDim.x));  // walkers per tile
-    const unsigned trh = (tr + 1) / 2;
     const unsigned ntiles = (W + tr - 1) / tr;
     const int nk = (d + 15) / 16;        // k-steps (and 16-column groups of the output) that hold data
     const unsigned half16 = lane >> 4;   // which of the warp's two walkers
@@ -145,66 +146,65 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             const unsigned w0 = tile * tr;
             // ------------------------------------------------ P1: proposals -> swizzled bf16 pieces
             // lane handles column pairs cp = ck + 16 e (columns 2cp, 2cp+1), e = 0..3: every load instruction of
-            // a half-warp reads 256 contiguous bytes of the row
-            // Two rows per half-warp are in flight at once (rows r and r + 64): all loads first, then the math.
-            for (unsigned rb = warp * 2 + half16; rb < trh; rb += 2 * (kFusedThreads / 32)) {
-                double2 xa[2][4], xb[2][4];
-                double zz[2];
-                bool live[2];
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    const unsigned r = rb + t * trh, w = w0 + r;
-                    live[t] = r < tr && w < W;
-                    zz[t] = 0.0;
-                    if (live[t]) {
-                        const unsigned i = p.shard_begin + w;
-                        const unsigned j = sm.j[tpar][r];
-                        zz[t] = sm.z[tpar][r];
-                        const double *xk = p.x + (a0 + i) * d, *xj = p.x + (size_t)j * d;
-#pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            const int c = 2 * (ck + 16 * e);
-                            xa[t][e] = make_double2(0.0, 0.0);
-                            xb[t][e] = make_double2(0.0, 0.0);
-                            if ((d & 1) == 0) {
-                                if (c < d) {
-                                    xa[t][e] = *reinterpret_cast<const double2 *>(xk + c);
-                                    xb[t][e] = __ldcg(reinterpret_cast<const double2 *>(xj + c));
-                                }
-                            } else {
-                                if (c < d) {
-                                    xa[t][e].x = xk[c];
-                                    xb[t][e].x = __ldcg(xj + c);
-                                }
-                                if (c + 1 < d) {
-                                    xa[t][e].y = xk[c + 1];
-                                    xb[t][e].y = __ldcg(xj + c + 1);
-                                }
-                            }
-                        }
-                    }
-                }
-#pragma unroll
-                for (int t = 0; t < 2; ++t) {
-                    if (!live[t]) continue;  // rows past the tile: whatever the buffer holds only reaches accumulator rows nobody reads
-                    const unsigned r = rb + t * trh;
-                    double v[8];
+            // a half-warp reads 256 contiguous bytes of the row.  Half-warp hw owns rows hw, hw+32, hw+64, hw+96 of
+            // the tile; the loads of the next row are issued before the math of the current one (two register
+            // buffers), so the L2 latency and the LSU work of one row hide behind the FP64 / conversion work of another.
+            {
+                const unsigned hw = warp * 2 + half16;
+                auto row_live = [&](unsigned r) { return r < tr && w0 + r < W; };
+                auto row_load = [&](unsigned r, double2 (&xa)[4], double2 (&xb)[4]) {
+                    const unsigned i = p.shard_begin + w0 + r;
+                    const double *xk = p.x + (a0 + i) * d, *xj = p.x + (size_t)sm.j[tpar][r] * d;
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const int c = 2 * (ck + 16 * e);
-                        v[2 * e] = (c < d) ? dadd(xb[t][e].x, dmul(zz[t], dsub(xa[t][e].x, xb[t][e].x))) - fp.mu[c] : 0.0;  // :255, centred
-                        v[2 * e + 1] = (c + 1 < d) ? dadd(xb[t][e].y, dmul(zz[t], dsub(xa[t][e].y, xb[t][e].y))) - fp.mu[c + 1] : 0.0;
+                        xa[e] = make_double2(0.0, 0.0);
+                        xb[e] = make_double2(0.0, 0.0);
+                        if ((d & 1) == 0) {
+                            if (c < d) {
+                                xa[e] = *reinterpret_cast<const double2 *>(xk + c);
+                                xb[e] = __ldcg(reinterpret_cast<const double2 *>(xj + c));
+                            }
+                        } else {
+                            if (c < d) {
+                                xa[e].x = xk[c];
+                                xb[e].x = __ldcg(xj + c);
+                            }
+                            if (c + 1 < d) {
+                                xa[e].y = xk[c + 1];
+                                xb[e].y = __ldcg(xj + c + 1);
+                            }
+                        }
                     }
+                };
+                auto row_emit = [&](unsigned r, const double2 (&xa)[4], const double2 (&xb)[4]) {
+                    const double zz = sm.z[tpar][r];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
+                        const int c = 2 * (ck + 16 * e);
+                        const double2 m = *reinterpret_cast<const double2 *>(sm.mu + c);  // zero past d
+                        // :255, centred; columns past d were loaded as zeros and stay zero
+                        const double v0 = dadd(xb[e].x, dmul(zz, dsub(xa[e].x, xb[e].x))) - m.x;
+                        const double v1 = dadd(xb[e].y, dmul(zz, dsub(xa[e].y, xb[e].y))) - m.y;
                         unsigned pk[PIECES];
-                        split3_pair(v[2 * e], v[2 * e + 1], pk);
+                        split3_pair(v0, v1, pk);
                         const unsigned cp = ck + 16 * e;  // column pair -> 4 bytes inside chunk cp/4
                         const unsigned off = sw128_chunk_offset(r, cp >> 2) + ((cp & 3) << 2);
 #pragma unroll
                         for (int pc = 0; pc < PIECES; ++pc) *reinterpret_cast<unsigned *>(sm.c[pc] + off) = pk[pc];
                     }
-                }
+                };
+                // rows past the tile are skipped: whatever the buffer holds there only reaches accumulator rows nobody reads
+                double2 xa0[4], xb0[4], xa1[4], xb1[4];
+                const bool l0 = row_live(hw), l1 = row_live(hw + 32), l2 = row_live(hw + 64), l3 = row_live(hw + 96);
+                if (l0) row_load(hw, xa0, xb0);
+                if (l1) row_load(hw + 32, xa1, xb1);
+                if (l0) row_emit(hw, xa0, xb0);
+                if (l2) row_load(hw + 64, xa0, xb0);
+                if (l1) row_emit(hw + 32, xa1, xb1);
+                if (l3) row_load(hw + 96, xa1, xb1);
+                if (l2) row_emit(hw + 64, xa0, xb0);
+                if (l3) row_emit(hw + 96, xa1, xb1);
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> tensor-core proxy
             __syncthreads();
