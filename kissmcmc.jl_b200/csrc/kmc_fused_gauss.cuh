@@ -28,10 +28,6 @@ namespace kmc {
 namespace tc {
 
 constexpr int kFusedThreads = 512;
-#ifndef KMC_K2F_P3FLIGHT
-#define KMC_K2F_P3FLIGHT 1
-#endif
-constexpr int kP3Flight = KMC_K2F_P3FLIGHT;  // listed rows per half-warp in flight in P3
 
 struct __align__(1024) FusedSmem {
     unsigned char a[PIECES][GPIECE_BYTES];  // matrix pieces (B operand), resident
@@ -127,20 +123,23 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
         const size_t a0 = batch ? (size_t)p.nhalf : 0;
 
         // draws (src/samplers.jl:250,:252,:260) of one tile: one thread per walker row, into parity `par`
-        auto tile_draws = [&](unsigned tl, unsigned par, unsigned r) {
+        auto tile_draws = [&](long long hs, unsigned tl, unsigned par, unsigned r) {
             const unsigned w = tl * tr + r;
             if (r < tr && w < W) {
                 unsigned j;
                 double z, u;
-                step_draws<REPLAY>(p, h, p.shard_begin + w, j, z, u);
+                step_draws<REPLAY>(p, hs, p.shard_begin + w, j, z, u);
                 sm.z[par][r] = z;
                 sm.u[par][r] = u;
                 sm.j[par][r] = j;
                 sm.q[par][r] = filter_q<REPLAY>(p, z, u);
             }
         };
-        if (blockIdx.x < ntiles && tid < BM) tile_draws(blockIdx.x, tpar, tid);
-        __syncthreads();
+        // the first tile's draws of this half-step were made in the shadow of the previous grid barrier
+        if (h == p.h0) {
+            if (blockIdx.x < ntiles && tid < BM) tile_draws(h, blockIdx.x, tpar, tid);
+            __syncthreads();
+        }
         K2F_TICK(0);
         for (unsigned tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const unsigned w0 = tile * tr;
@@ -234,6 +233,9 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                 tc_commit(&sm.mma_done);
             }
             if (warp < 4) {
+                double p0 = 0.0;  // current log-density: fetched while the GEMM runs
+                if ((unsigned)(warp * 32 + lane) < tr && w0 + warp * 32 + lane < W)
+                    p0 = p.lp[a0 + p.shard_begin + w0 + warp * 32 + lane];
                 mbar_wait(&sm.mma_done, mma_phase);
                 K2F_TICK(5);
                 __syncwarp();  // lane 0 came here from the MMA issue: converge before the .aligned TMEM loads
@@ -259,7 +261,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                 if ((unsigned)r < tr && w < W) {
                     const unsigned i = p.shard_begin + w;
                     const size_t k = a0 + i;
-                    const double p1 = fp.lognorm - 0.5 * ss, p0 = p.lp[k];
+                    const double p1 = fp.lognorm - 0.5 * ss;
                     // :260 -- the FP32 filter of kmc_kernels.cuh decides exactly like the FP64 expression whenever
                     // |tt| is above its rigorous margin; everything else takes the FP64 expression itself
                     const double tt = (p1 - p0) + (double)sm.q[tpar][r] * 0.6931471805599453;
@@ -271,7 +273,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     if (acc || store) sm.list[tpar][atomicAdd(&sm.nlist[tpar], 1u)] = (unsigned char)r;
                     if (acc) {
                         p.lp[k] = p1;
-                        p.nacc[k] += 1u;
+                        if (!(batch == 1 && n == 0)) atomicAdd(p.nacc + k, 1u);  // fire-and-forget; only this thread touches the counter
                     }
                     if (batch == 1 && n == 0) {  // :285-288
                         p.nacc[i] = 0u;
@@ -281,7 +283,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                 }
             }
             else if (warp < 8) {  // idle during the GEMM: the NEXT tile's draws, into the other parity
-                if (tile + gridDim.x < ntiles) tile_draws(tile + gridDim.x, tpar ^ 1, (warp - 4) * 32 + lane);
+                if (tile + gridDim.x < ntiles) tile_draws(h, tile + gridDim.x, tpar ^ 1, (warp - 4) * 32 + lane);
             } else if (tid == 8 * 32) {
                 sm.nlist[tpar ^ 1] = 0u;  // the previous tile's P3 finished before the barrier that closed this tile's P1
             }
@@ -291,14 +293,15 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             // ------------------------------------------------ P3: accepted rows (and the chain)
             // No barrier after P3: the next tile's P1 only writes sm.c (free since the MMA completed) and the
             // OTHER parity of the per-row arrays; the bar.sync after that P1 orders everything else.
-            // Two listed rows per half-warp in flight (all loads first, then the math and the stores).
+            // One listed row per half-warp at a time (two in flight, or a load/compute pipeline as in P1, spill at the
+            // 128-register cap of a 512-thread CTA and were measured slower: 44 and 36 us per half-step against 21).
             const unsigned nl = sm.nlist[tpar];
-            for (unsigned l0 = warp * 2 + half16; l0 < nl; l0 += kP3Flight * 2 * (kFusedThreads / 32)) {
-                double2 xa[kP3Flight][4], xb[kP3Flight][4];
-                unsigned rr[kP3Flight];
-                bool live[kP3Flight], accr[kP3Flight];
+            for (unsigned l0 = warp * 2 + half16; l0 < nl; l0 += 2 * (kFusedThreads / 32)) {
+                double2 xa[1][4], xb[1][4];
+                unsigned rr[1];
+                bool live[1], accr[1];
 #pragma unroll
-                for (int t = 0; t < kP3Flight; ++t) {
+                for (int t = 0; t < 1; ++t) {
                     const unsigned l = l0 + t * 2 * (kFusedThreads / 32);
                     live[t] = l < nl;
                     rr[t] = live[t] ? sm.list[tpar][l] : 0u;
@@ -329,7 +332,7 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
                     }
                 }
 #pragma unroll
-                for (int t = 0; t < kP3Flight; ++t) {
+                for (int t = 0; t < 1; ++t) {
                     if (!live[t]) continue;
                     const unsigned i = p.shard_begin + w0 + rr[t];
                     double *xk = p.x + (a0 + i) * d;
@@ -369,13 +372,12 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
         if (h + 1 < p.h1) {  // the reference's join between the two half-ensemble sweeps (:248/:273)
             target += gridDim.x;
             __syncthreads();
-            if (gridDim.x > 1) {
-                if (tid == 0) {
-                    barrier_arrive(p.barrier);
-                    barrier_wait(p.barrier, target);
-                }
-                __syncthreads();
-            }
+            if (gridDim.x > 1 && tid == 0) barrier_arrive(p.barrier);
+            // in the barrier's shadow (independent of the other CTAs): the next half-step's first tile's draws, into
+            // the parity the next tile uses (the last tile's P3, which read the other parity, ended before the bar.sync)
+            if (blockIdx.x < ntiles && tid >= 32 && tid < 32 + BM) tile_draws(h + 1, blockIdx.x, tpar, tid - 32);
+            if (gridDim.x > 1 && tid == 0) barrier_wait(p.barrier, target);
+            __syncthreads();
         }
         K2F_TICK(4);
     }
