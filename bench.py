@@ -13,7 +13,7 @@ scaling); value = walker-steps of all ranks / max-over-ranks device time.
 value     device-timed (CUDA events on the launch stream), inputs already resident in HBM.
 e2e       the same metric through the public API with HOST buffers: pinned theta0s -> H2D ->
           initial log-densities -> run -> chain transpose -> D2H into pinned result buffers.
-roofline  of the dominant kernel (emcee_run_kernel): algorithmic bytes per launch
+roofline  of the dominant kernel (named in roofline.kernel): algorithmic bytes per launch
           (24d+24 per walker-step + 8d+8 per stored sample) over the
           launch duration measured with the library's own CUDA events on the launch stream.
 cpu_baseline / --impl reference: the Julia reference cannot run here (no Julia in the image);
@@ -59,6 +59,21 @@ WORKLOADS = {
 def b_step(d: int) -> int:
     """Algorithmic bytes per walker-step."""
     return 24 * d + 24
+
+
+def dominant_kernel(wl, tensor, launch_mode):
+    """Name of the kernel the roofline object describes (selection logic: csrc/kmc_api.cu, kmc_emcee_create/run)."""
+    d = wl["d"]
+    if d > 16:
+        if tensor:
+            return "tc::gaussian_fused_kernel" if launch_mode == 0 else \
+                "propose_split_kernel + tc::gaussian_tc_kernel + accept_kernel"
+        return "propose_kernel + gaussian_wide_logp_kernel + accept_kernel"
+    if launch_mode == 0 and wl["nw"] * (8 * d + 12) <= 148 * 200 * 1024:
+        return "emcee_smem_kernel"
+    if launch_mode == 0 and d >= 6 and d % 2 == 0:
+        return "emcee_bulk_kernel"
+    return "emcee_run_kernel"
 
 
 def make_inputs(wl, seed):
@@ -360,9 +375,7 @@ def main():
             "roofline": roof or {
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "kernel": "emcee_smem_kernel" if d <= 4 else ("emcee_run_kernel" if d <= 16 else
-                          "propose_kernel + gaussian_tc_kernel + accept_kernel" if tensor else
-                          "propose_kernel + gaussian_wide_logp_kernel + accept_kernel"),
+                "kernel": dominant_kernel(wl, tensor, args.launch_mode),
                 "algorithmic_bytes_per_launch": alg_bytes_per_step, "kernel_ms_per_launch": k_ms,
                 "note": "algorithmic bytes = (24d+24) per walker-step + (8d+8) per stored sample; a state that fits "
                         "L2 / shared memory makes frac against the HBM copy peak able to exceed 1",

@@ -182,3 +182,46 @@ def test_gaussian_matches_scipy(orc):
     xs = np.abs(pts[:, :1]) + 0.01
     np.testing.assert_allclose(orc.Density(name, d, params).eval(xs), lognorm(1.0).logpdf(xs[:, 0]), rtol=1e-12, atol=1e-13)
     assert np.isneginf(orc.Density(name, d, params).logpdf([-1.0])) and np.isneginf(orc.Density(name, d, params).logpdf([0.0]))
+
+
+@pytest.mark.parametrize("case,nw,niter,nburnin,nthin,a", [
+    ("exponential", 6, 6 * 9, 6 * 4, 2, 2.0),       # burn-in reset at n == 0, thinning
+    ("exponential3", 10, 10 * 7 + 3, 10 * 2 + 9, 1, 2.5),   # niter, nburnin not multiples of nw (÷ truncation)
+    ("rosenbrock", 8, 8 * 12, 0, 3, 2.0),           # no burn-in: the counters are never reset
+    ("mvn2", 12, 12 * 8, 12 * 8, 1, 1.5),           # everything is burn-in: zero samples, accept_ratio = 0/0
+    ("rosenbrock", 4, 4 * 5, 4 * 2, 4, 2.0),        # nthin larger than the post-burn-in run: zero samples
+])
+def test_oracle_equals_literal_julia_transliteration(orc, case, nw, niter, nburnin, nthin, a):
+    """The C oracle against tests/julia_literal.py, an independent statement-by-statement transliteration of
+    src/samplers.jl:188-293 (1-based ranges, circshift, push!, total-step arguments), on the same draws: bit-identical
+    chains, log-densities, decisions, counters and final state."""
+    from tests import julia_literal as jl
+    name, d, params, th0, rad = cases.plugin_specs()[case]
+    x0 = cases.ball(th0, rad, nw, 3)
+    nitw, nbw = niter // nw, nburnin // nw
+    want = orc.emcee(orc.Density(name, d, params), x0, nitw, nbw, nthin, a, seed=11, trace=True)
+    pdf = {"exponential": lambda: jl.exponential, "rosenbrock": lambda: (lambda t: jl.rosenbrock(t, *params)),
+           "gaussian": lambda: jl.gaussian(list(np.asarray(params, dtype=np.float64)), d)}[name]()
+    src = jl.ReplaySource(*want["trace"][:3])
+    th, ar, lps, blobs, nacc, xfin, pfin = jl.emcee(pdf, x0.tolist(), src, niter=niter, nburnin=nburnin, nthin=nthin,
+                                                    a_scale=a, sample_z=src.sample_z)
+    assert blobs is None and src.i == nitw * nw
+    ns = (nitw - nbw) // nthin
+    assert all(len(t) == ns for t in th)
+    assert np.array_equal(np.array(th, dtype=np.float64).reshape(nw, ns, d), want["chain_x"])
+    assert np.array_equal(np.array(lps, dtype=np.float64).reshape(nw, ns), want["chain_lp"])
+    assert nacc == want["naccept"].tolist()
+    assert np.array_equal(np.array(ar), want["accept_ratio"], equal_nan=True)
+    assert np.array_equal(np.array(xfin), want["x"]) and np.array_equal(np.array(pfin), want["lp"])
+
+
+def test_literal_g_helpers_equal_oracle(orc):
+    """g_pdf / cdf_g_inv (src/samplers.jl:224,:227): literal transliteration == C oracle, bit for bit."""
+    from tests import julia_literal as jl
+    rng = np.random.default_rng(4)
+    for a in (1.5, 2.0, 3.7):
+        for u in list(rng.random(50)) + [0.0, 1.0 - 2.0 ** -53]:
+            z = jl.cdf_g_inv(u, a)
+            assert z == orc.cdf_g_inv(u, a)
+            assert jl.g_pdf(z, a) == orc.g_pdf(z, a)
+        assert jl.g_pdf(a * 1.0001, a) == 0.0 == orc.g_pdf(a * 1.0001, a)
