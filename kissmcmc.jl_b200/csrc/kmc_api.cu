@@ -385,7 +385,8 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         TcPlan pl = tc_plan(dn, npts);
         pl.lp.part = sc.part;
         const long long ne = pl.lp.wpad * d;
-        kmc::tc::split_theta_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, sc.pieces, npts, pl.lp.wpad, d);
+        kmc::tc::split_theta_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, sc.pieces, npts, pl.lp.wpad, d,
+                                                                                       1.4426950408889634);
         CUtensorMap mapA;
         if (!make_map_bf16_k32(&mapA, sc.pieces, (unsigned long long)kmc::tc::PIECES * pl.lp.wpad, kmc::tc::BM))
             return cudaErrorInvalidValue;
@@ -559,11 +560,14 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                 cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
                 h->nsm = nsm > 0 ? nsm : 148;
                 if (exact) {
-                    std::vector<double> xty(d, 0.0);  // X^T y in FP64: the y_n s_n term is then an exact d-dot
+                    // X^T (y - 1/2) in FP64: the y_n s_n term and the s_n/2 term of softplus(s) = s/2 + |s|/2 +
+                    // log1p(e^-|s|) together are then an exact d-dot (logistic_tc_finish_kernel)
+                    std::vector<double> xty(d, 0.0);
                     const float *Xh = (const float *)data, *yh = Xh + N * d;
-                    for (long long n = 0; n < N; ++n)
-                        if (yh[n] != 0.0f)
-                            for (int c = 0; c < d; ++c) xty[c] += (double)yh[n] * (double)Xh[n * d + c];
+                    for (long long n = 0; n < N; ++n) {
+                        const double yc = (double)yh[n] - 0.5;
+                        for (int c = 0; c < d; ++c) xty[c] += yc * (double)Xh[n * d + c];
+                    }
                     e = dev_alloc(&h->d_Xbf, sizeof(__nv_bfloat16) * N * d, device);
                     if (e == cudaSuccess) e = dev_alloc(&h->d_xty, sizeof(double) * d, device);
                     if (e == cudaSuccess) e = cudaMemcpy(h->d_xty, xty.data(), sizeof(double) * d, cudaMemcpyHostToDevice);

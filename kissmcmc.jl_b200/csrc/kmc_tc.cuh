@@ -4,9 +4,9 @@
 //     (BASELINE.json configs[3]) fused with its softplus row reduction.
 //
 //       S[w][n] = theta_w . x_n          [W x 32] . [32 x N]   (N ~ 1e6 streamed, W = active half)
-//       out[w]  = sum_n softplus(S[w][n])
+//       out[w]  = sum_n ( |S[w][n]|/2 + log1p(exp(-|S[w][n]|)) )   = sum_n softplus(S) - sum_n S/2
 //
-//     The caller adds the exact FP64 terms  theta.(X^T y)  and the prior (logistic_tc_finish_kernel).
+//     The caller adds the exact FP64 terms  theta.(X^T (y - 1/2))  and the prior (logistic_tc_finish_kernel).
 //
 //   * operands: X is bf16 (the plugin requires bf16-representable data, checked at creation, so
 //     this is exact); theta (FP64) is split into three bf16 pieces hi+mid+lo (24 significant
@@ -20,7 +20,8 @@
 //                  (M=128, N=256, K=16) per tile = 3 pieces x 2 k-steps, lo piece first;
 //                  tcgen05.commit frees the smem stage and publishes the accumulator
 //       warps 2-9  epilogue: tcgen05.ld 32x32b.x32 from the double-buffered TMEM accumulator
-//                  (2 x 256 columns = all 512), softplus in FP32 on MUFU ex2/lg2, FP32 partial
+//                  (2 x 256 columns = all 512); per logit one MUFU ex2, one FFMA (running product of
+//                  1 + 2^-|s'|, one lg2 per 32 columns) and one FADD (sum of |s'|); FP32 partial
 //                  per 32 columns, FP64 running sum per row, tail columns masked
 //   * every mbarrier wait has a watchdog (trap after ~2 s) so a bad descriptor cannot hang the GPU.
 #pragma once
@@ -36,7 +37,12 @@ namespace kmc {
 namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4, ACC = 2, PIECES = 3;
-constexpr int kEpiWarps = 8;
+#ifndef KMC_K3_EPI
+#define KMC_K3_EPI 16
+#endif
+constexpr int kEpiWarps = KMC_K3_EPI;            // 8 or 16: 2 or 4 epilogue warps per scheduler
+constexpr int kEpiParts = kEpiWarps / 4;         // column parts of the accumulator (a warp owns 32 rows x BN/kEpiParts columns)
+constexpr int kEpiCols = BN / kEpiParts;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
 constexpr int kABytes = BM * BK * 2;  // 8 KB per theta piece
 constexpr int kBBytes = BN * BK * 2;  // 16 KB per X tile
@@ -46,7 +52,7 @@ struct __align__(1024) Smem {
     unsigned char b[STAGES][kBBytes];
     unsigned long long full[STAGES], empty[STAGES], tfull[ACC], tempty[ACC], afull, aempty;
     unsigned tmem_base;
-    double comb[BM];
+    double comb[kEpiParts - 1][BM];
 };
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -115,33 +121,37 @@ __host__ __device__ constexpr unsigned idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float softplus32(float s) {
-    // max(s,0) + ln2 * lg2(1 + 2^(-|s| log2 e))
-    float t, l;
-    const float a = -fabsf(s) * 1.4426950408889634f;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
-    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.0f + t));
-    return fmaf(l, 0.6931471805599453f, fmaxf(s, 0.0f));
+// 2^-|s|: one MUFU.EX2 (the abs / neg fold into the operand modifiers)
+__device__ __forceinline__ float ex2_neg_abs(float s) {
+    float t;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(-fabsf(s)));
+    return t;
 }
 
-// Same function with log1p(t), t in (0,1], as a degree-8 polynomial on the FMA pipe (max abs error
-// 1.2e-7 in FP32, like the MUFU version): one MUFU instead of two.  The epilogue alternates the two
-// variants column by column so that the XU pipe (16 lanes/clk/SM) and the FMA pipe / issue slots
-// are loaded evenly -- the all-MUFU epilogue ran the XU pipe at 86 % with the FMA pipe at 22 %.
-__device__ __forceinline__ float softplus32_poly(float s) {
-    float t;
-    const float a = -fabsf(s) * 1.4426950408889634f;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(a));
-    float r = -0.006006604991853237f;
-    r = fmaf(r, t, 0.03426460176706314f);
-    r = fmaf(r, t, -0.09229041635990143f);
-    r = fmaf(r, t, 0.1649981290102005f);
-    r = fmaf(r, t, -0.2394333779811859f);
-    r = fmaf(r, t, 0.33144664764404297f);
-    r = fmaf(r, t, -0.49982550740242004f);
-    r = fmaf(r, t, 0.999993622303009f);
-    r = fmaf(r, t, 3.910905377324525e-08f);
-    return r + fmaxf(s, 0.0f);
+// The same function on the FMA / ALU pipes (no MUFU): 2^-a = 2^-i * 2^(i-a), i = round(a) taken from the low mantissa
+// bits of a + 1.5*2^23, 2^x on [-1/2, 1/2] as a degree-5 polynomial (max relative error 2.0e-7, MUFU.EX2: 2.4e-7), the
+// exponent subtracted as an integer.  Every KMC_K3_POLY-th column of the epilogue takes this path so that the XU pipe
+// (16 lanes/clk/SM, the bound of the all-MUFU epilogue) and the issue slots are loaded evenly.
+#ifndef KMC_K3_POLY
+#define KMC_K3_POLY 4
+#endif
+__device__ __forceinline__ float ex2_neg_abs_poly(float s) {
+    const float a = fminf(fabsf(s), 126.0f);
+    const float r = a + 12582912.0f;
+    const float x = (r - 12582912.0f) - a;
+    float q = 0.0013266970636323094f;
+    q = fmaf(q, x, 0.009675459936261177f);
+    q = fmaf(q, x, 0.05550742521882057f);
+    q = fmaf(q, x, 0.24022121727466583f);
+    q = fmaf(q, x, 0.6931469440460205f);
+    q = fmaf(q, x, 1.0000001192092896f);
+    return __int_as_float(__float_as_int(q) - (__float_as_int(r) << 23));
+}
+// column j of a 32-column chunk (j is a compile-time constant after unrolling)
+__device__ __forceinline__ float ex2_neg_abs_col(float s, int j) {
+    constexpr int P = KMC_K3_POLY > 0 ? KMC_K3_POLY : 1;
+    if (KMC_K3_POLY > 0 && j % P == P - 1) return ex2_neg_abs_poly(s);
+    return ex2_neg_abs(s);
 }
 
 // 32 consecutive FP32 columns of this thread's TMEM lane -> registers (asynchronous until wait::ld)
@@ -266,7 +276,7 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // ===================== epilogue: softplus + row sums =====================
         const int ew = warp - 2;            // 0..7
         const int quarter = warp & 3;       // TMEM lanes this warp may access: 32*quarter .. +31
-        const int colhalf = ew >> 2;        // columns [0,128) or [128,256) of the accumulator
+        const int colpart = ew >> 2;        // which kEpiCols columns of the accumulator
         const int row = quarter * 32 + lane;
         unsigned acc = 0, accphase = 0;
         for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
@@ -277,31 +287,51 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                 mbar_wait(&sm.tfull[acc], accphase);
                 tc_fence_after();
                 const long long nvalid = p.N - (long long)t * BN;  // columns of this tile that are real data
-                // 4 chunks of 32 columns; the TMEM load of chunk c+1 is in flight while chunk c is reduced
+                // chunks of 32 columns; the TMEM load of chunk c+1 is in flight while chunk c is reduced.  (Carrying the
+                // prefetch across the tile boundary was measured slower: 1326 vs 1098 us per half-step -- the wait loop
+                // inside the unrolled chunk code costs the compiler its MUFU / FMA interleaving.)
                 unsigned v[2][32];
-                const unsigned tbase = tmem + ((unsigned)(quarter * 32) << 16) + acc * BN + colhalf * (BN / 2);
+                const unsigned tbase = tmem + ((unsigned)(quarter * 32) << 16) + acc * BN + colpart * kEpiCols;
                 tmem_ld32(tbase, v[0]);
 #pragma unroll
-                for (int c = 0; c < BN / 2 / 32; ++c) {
+                for (int c = 0; c < kEpiCols / 32; ++c) {
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c + 1 < BN / 2 / 32) tmem_ld32(tbase + (c + 1) * 32, v[(c + 1) & 1]);
-                    const int col0 = colhalf * (BN / 2) + c * 32;
+                    if (c + 1 < kEpiCols / 32) tmem_ld32(tbase + (c + 1) * 32, v[(c + 1) & 1]);
+                    const int col0 = colpart * kEpiCols + c * 32;
                     const unsigned *vv = v[c & 1];
-                    float part = 0.0f, part2 = 0.0f;
+                    // softplus(s) = s/2 + |s|/2 + log1p(e^-|s|).  The s/2 term is linear in theta and lives in the exact
+                    // FP64 d-dot of the finish kernel; the logits arrive in log2 units (theta was scaled by log2 e before
+                    // the split), so the rest is  ln2 * ( |s'|/2 + lg2(1 + 2^-|s'|) ).  The 32 logarithms of a chunk are
+                    // taken as ONE lg2 of the running product of (1 + t), t in (0,1] -- at most 2^16 per chain, no
+                    // overflow: one MUFU (ex2) + one FFMA + one FADD per logit instead of two MUFU + ~7 FMA-pipe slots.
+                    float pa = 1.0f, pb = 1.0f, sa = 0.0f, sb = 0.0f;
                     if (nvalid >= col0 + 32) {
 #pragma unroll
-                        for (int j = 0; j < 32; j += 2) {  // MUFU and FMA-pipe variants alternate
-                            part += softplus32(__uint_as_float(vv[j]));
-                            part2 += softplus32_poly(__uint_as_float(vv[j + 1]));
+                        for (int j = 0; j < 32; j += 2) {
+                            const float s0 = __uint_as_float(vv[j]), s1 = __uint_as_float(vv[j + 1]);
+                            const float t0 = ex2_neg_abs_col(s0, j), t1 = ex2_neg_abs_col(s1, j + 1);
+                            pa = fmaf(pa, t0, pa);
+                            pb = fmaf(pb, t1, pb);
+                            sa += fabsf(s0);
+                            sb += fabsf(s1);
                         }
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            if (col0 + j < nvalid) part += softplus32(__uint_as_float(vv[j]));
-                            if (col0 + j + 1 < nvalid) part2 += softplus32_poly(__uint_as_float(vv[j + 1]));
+                            const float s0 = __uint_as_float(vv[j]), s1 = __uint_as_float(vv[j + 1]);
+                            if (col0 + j < nvalid) {
+                                pa = fmaf(pa, ex2_neg_abs_col(s0, j), pa);
+                                sa += fabsf(s0);
+                            }
+                            if (col0 + j + 1 < nvalid) {
+                                pb = fmaf(pb, ex2_neg_abs_col(s1, j + 1), pb);
+                                sb += fabsf(s1);
+                            }
                         }
                     }
-                    rowsum += (double)part + (double)part2;
+                    float lg;
+                    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(lg) : "f"(pa * pb));
+                    rowsum += (double)fmaf(0.5f, sa + sb, lg);  // log2 units; scaled by ln 2 at the store
                 }
                 tc_fence_before();
                 __syncwarp();
@@ -311,13 +341,15 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     accphase ^= 1;
                 }
             }
-            // combine the two column halves of each row, then one store per (chunk, row)
+            // combine the column parts of each row in fixed order, then one store per (chunk, row)
             asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
-            if (colhalf == 1) sm.comb[row] = rowsum;
+            if (colpart > 0) sm.comb[colpart - 1][row] = rowsum;
             asm volatile("bar.sync 1, %0;" ::"r"(kEpiWarps * 32));
-            if (colhalf == 0) {
+            if (colpart == 0) {
                 const long long w = (long long)mt * BM + row;
-                if (w < p.W) p.part[(size_t)ch * p.W + w] = rowsum + sm.comb[row];
+#pragma unroll
+                for (int k = 0; k < kEpiParts - 1; ++k) rowsum += sm.comb[k][row];
+                if (w < p.W) p.part[(size_t)ch * p.W + w] = rowsum * 0.6931471805599453;
             }
         }
     }
@@ -329,11 +361,11 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
 // theta (FP64) -> three bf16 pieces hi + mid + lo, rows padded with zeros to wpad.
 __global__ void split_theta_kernel(const double *__restrict__ TH, __nv_bfloat16 *__restrict__ out, long long W,
-                                   long long wpad, int d) {
+                                   long long wpad, int d, double scale) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= wpad * d) return;
     const long long w = e / d;
-    double r = w < W ? TH[e] : 0.0;
+    double r = w < W ? TH[e] * scale : 0.0;  // scale = log2 e: the GEMM delivers the logits in log2 units
 #pragma unroll
     for (int pc = 0; pc < PIECES; ++pc) {
         const __nv_bfloat16 h = __double2bfloat16(r);
@@ -347,7 +379,8 @@ __global__ void f32_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *
     if (e < n) out[e] = __float2bfloat16(in[e]);
 }
 
-// logp = theta . (X^T y) - sum softplus - |theta|^2 / (2 sigma^2); chunks summed in fixed order.
+// logp = theta . (X^T (y - 1/2)) - sum_n (|s_n|/2 + log1p(e^-|s_n|)) - |theta|^2 / (2 sigma^2)
+//      = theta . (X^T y) - sum_n softplus(s_n) - prior;   xty holds X^T (y - 1/2); chunks summed in fixed order.
 __global__ void logistic_tc_finish_kernel(const double *__restrict__ TH, const double *__restrict__ part,
                                           const double *__restrict__ xty, double *__restrict__ out, long long W, int d,
                                           int nchunks, double inv2s2) {
