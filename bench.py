@@ -154,14 +154,9 @@ def run_reference(args, wl):
         return 0
     from oracle import oracle
     nthreads = os.cpu_count() or 1
-    params, x0 = make_inputs(wl, 1)
-    dens = oracle.Density(wl["plugin"], wl["d"], params, data=wl.get("_data"))
-    nw = wl["nw"]
-    # calibrate so one step is ~4 s of CPU work (the whole run stays within a few minutes)
-    t0 = time.perf_counter()
-    oracle.emcee(dens, x0, 2, 1, 1, 2.0, seed=1, store=False, nthreads=nthreads, native=True)
-    per_iter = max((time.perf_counter() - t0) / 2, 1e-6)
-    iters = int(max(2, min(wl["niter_walker"], 4.0 / per_iter)))
+    # each step ~4 s of CPU work (the whole run stays within a few minutes)
+    dens, x0, nw, iters = _cpu_sample(wl, 4.0, nthreads)
+    iters, _ = _cpu_run(wl, dens, x0, iters, 4.0, nthreads, 99)      # settles the sample size (untimed)
     times = []
     for i in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -171,7 +166,8 @@ def run_reference(args, wl):
             times.append(time.perf_counter() - t0)
     total = sum(times)
     value = nw * iters * args.steps / total
-    sample = f"{wl['plugin']} d={wl['d']}, {nw} walkers x {iters} iterations per step (of {wl['niter_walker']})"
+    sample = (f"{wl['plugin']} d={wl['d']}, {nw} walkers (of {wl['nw']}) x {iters} iterations per step "
+              f"(of {wl['niter_walker']})")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -187,21 +183,59 @@ def run_reference(args, wl):
     return 0
 
 
-def cpu_baseline(wl, seconds=12.0):
+def _cpu_sample(wl, seconds, nthreads):
+    """Bounded sample of the workload for the CPU leg: (walkers, iterations) worth ~`seconds` of host time.
+    Calibrated in two steps (single-thread cost on the smallest legal ensemble, then all threads on a sub-ensemble
+    sized from it) so that even the calibration of an expensive density stays short; the sample keeps the full
+    ensemble unless two iterations of it would already exceed the budget."""
     from oracle import oracle
-    nthreads = os.cpu_count() or 1
     params, x0 = make_inputs(wl, 1)
     dens = oracle.Density(wl["plugin"], wl["d"], params, data=wl.get("_data"))
+    nw = wl["nw"]
+    # 1) one thread, the smallest legal ensemble: a reliable per-walker-step cost without OpenMP noise
+    n1 = min(nw, 2 * ((wl["d"] + 3) // 2))
+    oracle.emcee(dens, x0[:n1], 1, 0, 1, 2.0, seed=1, store=False, nthreads=1, native=True)   # library load
     t0 = time.perf_counter()
-    oracle.emcee(dens, x0, 2, 1, 1, 2.0, seed=1, store=False, nthreads=nthreads, native=True)
-    per_iter = max((time.perf_counter() - t0) / 2, 1e-6)
-    iters = int(max(2, min(wl["niter_walker"], seconds / per_iter)))
-    t0 = time.perf_counter()
-    oracle.emcee(dens, x0, iters, iters // 2, max(1, iters // 5), 2.0, seed=2, store=True, nthreads=nthreads,
-                 native=True)
-    dt = time.perf_counter() - t0
-    return {"value": wl["nw"] * iters / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": f"{wl['plugin']} d={wl['d']}, {wl['nw']} walkers x {iters} iterations "
+    oracle.emcee(dens, x0[:n1], 1, 0, 1, 2.0, seed=1, store=False, nthreads=1, native=True)
+    per_ws1 = max((time.perf_counter() - t0) / n1, 1e-9)
+    # 2) all threads on a sub-ensemble sized for ~0.5 s if the threads scaled perfectly (best of 2)
+    ncal = int(min(nw, max(n1, 0.5 * nthreads / (2 * per_ws1))))
+    ncal -= ncal % 2
+    dt = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        oracle.emcee(dens, x0[:ncal], 2, 1, 1, 2.0, seed=1, store=False, nthreads=nthreads, native=True)
+        dt = min(dt, time.perf_counter() - t0)
+    per_ws = max(dt / (2 * ncal), 1e-9)
+    nw_s = nw
+    if 2 * nw * per_ws > 1.5 * seconds:
+        nw_s = int(max(ncal, min(nw, seconds / (2 * per_ws))))
+        nw_s -= nw_s % 2
+    iters = int(max(2, min(wl["niter_walker"], seconds / (per_ws * nw_s))))
+    return dens, x0[:nw_s], nw_s, iters
+
+
+def _cpu_run(wl, dens, x0, iters, seconds, nthreads, seed):
+    """One timed CPU sample; if the calibration was pessimistic (a noisy host makes small OpenMP regions look slow)
+    and the run ended in under a third of the budget, lengthen it and time again (at most twice)."""
+    from oracle import oracle
+    for _ in range(3):
+        t0 = time.perf_counter()
+        oracle.emcee(dens, x0, iters, iters // 2, max(1, iters // 5), 2.0, seed=seed, store=True, nthreads=nthreads,
+                     native=True)
+        dt = time.perf_counter() - t0
+        if dt >= seconds / 3 or iters >= wl["niter_walker"]:
+            break
+        iters = int(min(wl["niter_walker"], max(iters + 1, iters * 0.8 * seconds / max(dt, 1e-6))))
+    return iters, dt
+
+
+def cpu_baseline(wl, seconds=12.0):
+    nthreads = os.cpu_count() or 1
+    dens, x0, nw_s, iters = _cpu_sample(wl, seconds, nthreads)
+    iters, dt = _cpu_run(wl, dens, x0, iters, seconds, nthreads, 2)
+    return {"value": nw_s * iters / dt, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": f"{wl['plugin']} d={wl['d']}, {nw_s} walkers (of {wl['nw']}) x {iters} iterations "
                       f"(of {wl['niter_walker']}), {dt:.1f} s, C restatement of the reference loop with OpenMP"}
 
 

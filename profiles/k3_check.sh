@@ -1,11 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-source profiles/capture_final.sh.lib
-for V in x_e16_p4 e16_p4; do
-  KMC_LIB=$PWD/build/variants/libkmc_$V.so timeout 120 python profiles/k3_variants.py > gpurun_out/k3_variant_$V.log 2>&1
-  tail -4 gpurun_out/k3_variant_$V.log
-done
-for V in x_e16_p4; do
-  export KMC_LIB=$PWD/build/variants/libkmc_$V.so
-  SKIP=2 cap k3_$V logistic_tc_kernel python profiles/prof_run.py logistic32d 2 0
-done
+./build/mb/ffma2_bench > gpurun_out/ffma2_bench.log 2>&1; cat gpurun_out/ffma2_bench.log
+KMC_TC=1 KMC_LIB=$PWD/build/variants/libkmc_k2fprof.so timeout 60 python profiles/prof_run.py gaussian100d 200 0 > gpurun_out/k2f_phase_cycles.log 2>&1; tail -8 gpurun_out/k2f_phase_cycles.log
+timeout 300 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_k3.log 2>&1; tail -3 gpurun_out/pytest_k3.log
+timeout 150 python bench.py --workload logistic32d --steps 5 --warmup 3 > gpurun_out/bench_logistic32d.json 2> gpurun_out/bench_logistic32d.err; cat gpurun_out/bench_logistic32d.json
