@@ -209,28 +209,36 @@ gaussian_fused_kernel(const __grid_constant__ CUtensorMap mapA, const RunParams 
             __syncthreads();
             K2F_TICK(1);
             // ------------------------------------------------ P2: tcgen05 GEMM, epilogue, accept
-#ifdef KMC_K2F_ELECT
-            if (warp == 0 && elect_one()) {
-#else
-            if (tid == 0) {
-#endif
+            if (warp == 0) {
+                // The WHOLE warp runs the issue loop, converged: every operand (descriptors, TMEM address, instruction
+                // descriptor) is warp-uniform and stays in uniform registers, and the one elected lane is a predicate on
+                // the tcgen05 instructions themselves.  Issued from inside `if (tid == 0)` each MMA cost an ELECT /
+                // BRA.U.ANY waterfall and ~18 instructions (~100 cycles against the 56-cycle tensor floor of a
+                // 128x112x16 MMA: the issue stream, not the tensor pipe, paced the GEMM).  A descriptor of a later
+                // k-step is the piece's descriptor plus a compile-time constant in its 16-byte address field.
                 tc_fence_after();
+                const unsigned leader = elect_one() ? 1u : 0u;
                 // only the first ceil(d/16) k-steps and ceil(d/16)*16 output columns: the rest are zero padding
                 // (adding +0 products changes no bit, so this equals the full 128x128x128 product)
                 const unsigned idesc = idesc_bf16_f32(BM, nk * 16);
+                unsigned long long dc[PIECES], da[PIECES];
+#pragma unroll
+                for (int pc = 0; pc < PIECES; ++pc) {
+                    dc[pc] = smem_desc_sw128(smem_u32(sm.c[pc]));
+                    da[pc] = smem_desc_sw128(smem_u32(sm.a[pc]));
+                }
                 const int pc_c[6] = {2, 0, 1, 1, 0, 0};
                 const int pc_a[6] = {0, 2, 1, 0, 1, 0};
 #pragma unroll
                 for (int pr = 0; pr < 6; ++pr) {
-                    const unsigned cb = smem_u32(sm.c[pc_c[pr]]), ab = smem_u32(sm.a[pc_a[pr]]);
 #pragma unroll
                     for (int k = 0; k < GK / 16; ++k) {
                         if (k >= nk) break;
-                        const unsigned off = (k >> 2) * (GPIECE_BYTES / 2) + (k & 3) * 32;
-                        tc_mma(tmem, smem_desc_sw128(cb + off), smem_desc_sw128(ab + off), idesc, (pr | k) ? 1u : 0u);
+                        const unsigned long long off16 = (unsigned long long)(((k >> 2) * (GPIECE_BYTES / 2) + (k & 3) * 32) >> 4);
+                        tc_mma_elect(tmem, dc[pc_c[pr]] + off16, da[pc_a[pr]] + off16, idesc, (pr | k) ? 1u : 0u, leader);
                     }
                 }
-                tc_commit(&sm.mma_done);
+                tc_commit_elect(&sm.mma_done, leader);
             }
             if (warp < 4) {
                 double p0 = 0.0;  // current log-density: fetched while the GEMM runs

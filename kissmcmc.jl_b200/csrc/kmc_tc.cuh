@@ -105,6 +105,28 @@ __device__ __forceinline__ void tc_mma(unsigned tmem_d, unsigned long long adesc
         : "memory");
 }
 
+// The same two instructions for a converged warp: every lane executes the asm with warp-uniform operands, only the
+// elected lane (leader != 0) issues.  No divergent branch around the instruction, so ptxas keeps the operands in
+// uniform registers instead of an ELECT / BRA.U.ANY waterfall per MMA.
+__device__ __forceinline__ void tc_mma_elect(unsigned tmem_d, unsigned long long adesc, unsigned long long bdesc,
+                                             unsigned idesc, unsigned accumulate, unsigned leader) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "setp.ne.b32 q, %5, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(unsigned long long *bar, unsigned leader) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(leader)
+        : "memory");
+}
+
 // K-major operand tile with 64-byte rows (32 bf16), SWIZZLE_64B: 8-row groups are 512 B apart
 // (SBO), LBO unused (1), descriptor version 1 (sm_100), layout type 4.  cute/arch/mma_sm100_desc.hpp.
 __device__ __forceinline__ unsigned long long smem_desc_sw64(unsigned addr) {
