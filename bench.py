@@ -230,7 +230,7 @@ def _cpu_run(wl, dens, x0, iters, seconds, nthreads, seed):
     return iters, dt
 
 
-def cpu_baseline(wl, seconds=12.0):
+def cpu_baseline(wl, seconds=15.0):
     nthreads = os.cpu_count() or 1
     dens, x0, nw_s, iters = _cpu_sample(wl, seconds, nthreads)
     iters, dt = _cpu_run(wl, dens, x0, iters, seconds, nthreads, 2)
