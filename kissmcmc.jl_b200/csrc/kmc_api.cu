@@ -18,6 +18,7 @@
 #include "kmc_batched.cuh"
 #include "kmc_tc.cuh"
 #include "kmc_fused_gauss.cuh"
+#include "kmc_fused_gauss2.cuh"
 #include "kmc_kernels.cuh"
 
 namespace {
@@ -218,6 +219,7 @@ struct kmc_density_s {
     int nsm = 148;
     // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
     __nv_bfloat16 *d_Abf = nullptr;
+    int fused_variant = 1;       // dense Gaussian, launch_mode 0: 1 = K2F (matrix in shared memory), 2 = K2G (matrix in TMEM)
     CUtensorMap mapA;
     double *d_At = nullptr;  // FP64 kernel: A transposed and padded to 128 rows, [d][128]
 };
@@ -595,6 +597,11 @@ int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value) {
         h->tc_on = value != 0.0;
         return KMC_OK;
     }
+    if (!strcmp(key, "fused_variant")) {
+        if (value != 1.0 && value != 2.0) return fail(KMC_ERR_INVALID, "fused_variant must be 1 (K2F) or 2 (K2G)");
+        h->fused_variant = (int)value;
+        return KMC_OK;
+    }
     return fail(KMC_ERR_INVALID, "unknown option '%s'", key);
 }
 
@@ -606,6 +613,10 @@ int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value) {
     }
     if (!strcmp(key, "batched")) {
         *value = h->ops.batch;
+        return KMC_OK;
+    }
+    if (!strcmp(key, "fused_variant")) {
+        *value = h->fused_variant;
         return KMC_OK;
     }
     return fail(KMC_ERR_INVALID, "unknown info key '%s'", key);
@@ -961,6 +972,28 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
     if (s->dn->ops.batch) {  // propose -> batched log-density -> accept, per half-step
         const unsigned grid = (unsigned)((s->scnt * 32 + 255) / 256);
         const bool gtc = s->dn->ops.batch == 1 && s->dn->tc_ok && s->dn->tc_on;  // Y-free tcgen05 Gaussian pipeline
+        if (gtc && s->opts.launch_mode == 0 && s->dn->fused_variant == 2) {  // K2G: K2F with the matrix resident in TMEM
+            kmc::tc::Fused2Params fpar{};
+            fpar.mu = s->dn->d_params;
+            fpar.apieces = reinterpret_cast<const unsigned *>(s->dn->d_Abf);
+            fpar.lognorm = s->dn->params[s->d + (size_t)s->d * s->d];
+            fpar.d = s->d;
+            const size_t smem = sizeof(kmc::tc::Fused2Smem) + 1024;
+            const void *kern = replay ? (const void *)kmc::tc::gaussian_fused2_kernel<true>
+                                      : (const void *)kmc::tc::gaussian_fused2_kernel<false>;
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const long long ntiles = (s->scnt + kmc::tc::BM - 1) / kmc::tc::BM;
+            const unsigned fgrid = (unsigned)std::min<long long>(ntiles, s->dn->nsm);
+            set_range(hbeg, hend);
+            void *fargs[] = {&p, &fpar};
+            CU_TRY(cudaLaunchCooperativeKernel(kern, dim3(fgrid), dim3(kmc::tc::kFusedThreads), fargs, smem, s->stream));
+            s->bar_base += (unsigned long long)(hend - hbeg - 1) * fgrid;
+            s->last_launches += 1;
+            CU_TRY(cudaEventRecord(s->ev1, s->stream));
+            s->timed = true;
+            s->hdone = hend;
+            return KMC_OK;
+        }
         if (gtc && s->opts.launch_mode == 0) {  // K2F: the whole range of half-steps in one persistent fused kernel
             kmc::tc::FusedParams fpar{};
             fpar.mu = s->dn->d_params;

@@ -17,6 +17,8 @@ ld = km.LogDensity(wl["plugin"], wl["d"], params, data=wl.get("_data"))
 import os
 if os.environ.get("KMC_TC") is not None:
     ld.set_option("tensor_cores", int(os.environ["KMC_TC"]))
+if os.environ.get("KMC_FUSED_VARIANT") is not None:
+    ld.set_option("fused_variant", int(os.environ["KMC_FUSED_VARIANT"]))
 print("tensor_cores:", ld.info("tensor_cores"))
 for rep in range(3):
     s = km.Sampler(ld, x0, iters, iters // 2, max(1, iters // 4), 2.0, seed=rep, launch_mode=mode)

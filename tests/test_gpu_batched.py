@@ -242,3 +242,54 @@ def test_gaussian_fused_kernel_equals_three_kernel_pipeline(km):
         for a, b in zip(*out):
             assert np.array_equal(a, b)
         assert 0.02 < out[0][2].mean() < 0.9
+
+
+def test_gaussian_fused_tmem_variant(km, orc):
+    """K2G (fused_variant 2: matrix pieces resident in TMEM as the A operand, walker pieces double-buffered, the GEMM
+    of a tile hidden behind the next tile's proposal phase) against K2F on the same Philox draws.  The two sum |y|^2 in
+    a different order (FP32 lane tree vs column-sequential), so log-densities agree to the tensor path's stated
+    tolerance 1e-5 (1 + |y|^2) and a decision can differ only within that distance of a tie: nearly every walker ends
+    bit-identical.  Sizes: partial tiles, one / two / three tiles per CTA, odd d.  Replay against the oracle as well."""
+    for d, nw in ((100, 2 * 1000), (33, 2 * 130), (64, 2 * 128 * 150), (100, 2 * (148 * 128 * 2 + 777))):
+        prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
+        ld = km.LogDensity("gaussian", d, prm)
+        ld.set_option("tensor_cores", 1)
+        x0 = np.linspace(-1, 1, d) + cases.ball(np.zeros(d), 0.7, nw, 5)
+        out = []
+        for variant in (1, 2):
+            ld.set_option("fused_variant", variant)
+            assert ld.info("fused_variant") == float(variant)
+            s = km.Sampler(ld, x0, 6, 2, 2, 2.0, 77)
+            s.run(2)
+            s.run(-1)
+            th, lp, ar = s.results()
+            x, l, na = s.state()
+            s.close()
+            out.append((th, lp, ar, x, l, na))
+        (th1, lp1, ar1, x1, l1, na1), (th2, lp2, ar2, x2, l2, na2) = out
+        same = np.all(x1 == x2, axis=1)
+        assert same.mean() > 0.995, (d, nw, same.mean())
+        ss = 2.0 * (prm[-1] - l1[same])
+        assert np.all(np.abs(l2[same] - l1[same]) <= 1e-5 * (1.0 + ss))
+        assert np.all(np.isfinite(l2)) and abs(ar2.mean() - ar1.mean()) < 0.01
+        first = np.all(th1[:, 0] == th2[:, 0], axis=1)     # the first stored sample (after 3 iterations)
+        assert first.mean() > 0.997
+    # replay mode against the oracle's exact FP64 run
+    d, nw, nitw = 40, 200, 9
+    prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
+    ld, od = km.LogDensity("gaussian", d, prm), orc.Density("gaussian", d, prm)
+    ld.set_option("tensor_cores", 1)
+    ld.set_option("fused_variant", 2)
+    x0 = cases.ball(np.zeros(d), 0.5, nw, 5)
+    want = orc.emcee(od, x0, nitw, 0, 1, 2.0, seed=21, trace=True, nthreads=4)
+    s = km.Sampler(ld, x0, nitw, 0, 1, 2.0, 21, km.MODE_REPLAY)
+    s.set_replay(*want["trace"][:3])
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    same = na == want["naccept"]
+    assert same.mean() > 0.98
+    if same.all():
+        assert np.array_equal(th, want["chain_x"]) and np.array_equal(x, want["x"])
+        assert np.all(np.abs(lp - want["chain_lp"]) <= 1e-5 * (1.0 + 2.0 * (prm[-1] - want["chain_lp"])))
