@@ -66,7 +66,7 @@ def dominant_kernel(wl, tensor, launch_mode):
     d = wl["d"]
     if d > 16:
         if tensor:
-            return "tc::gaussian_fused_kernel" if launch_mode == 0 else \
+            return "tc::gaussian_fused2_kernel" if launch_mode == 0 else \
                 "propose_split_kernel + tc::gaussian_tc_kernel + accept_kernel"
         return "propose_kernel + gaussian_wide_logp_kernel + accept_kernel"
     if launch_mode == 0 and wl["nw"] * (8 * d + 12) <= 148 * 200 * 1024:

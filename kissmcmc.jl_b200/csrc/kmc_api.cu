@@ -219,7 +219,7 @@ struct kmc_density_s {
     int nsm = 148;
     // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
     __nv_bfloat16 *d_Abf = nullptr;
-    int fused_variant = 1;       // dense Gaussian, launch_mode 0: 1 = K2F (matrix in shared memory), 2 = K2G (matrix in TMEM)
+    int fused_variant = 2;       // dense Gaussian, launch_mode 0: 2 = K2G (matrix in TMEM, default), 1 = K2F (matrix in shared memory)
     CUtensorMap mapA;
     double *d_At = nullptr;  // FP64 kernel: A transposed and padded to 128 rows, [d][128]
 };

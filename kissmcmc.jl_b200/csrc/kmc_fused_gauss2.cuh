@@ -36,6 +36,7 @@ namespace tc {
 constexpr int kRowBufs = 3;            // per-row draw arrays: tile k uses buffer k % 3 (E(k-1) | draws(k+1) | P1(k))
 constexpr unsigned kTmemA = 0;         // matrix pieces: piece pc at columns 64*pc .. 64*pc+63
 constexpr unsigned kTmemD = 192;       // accumulators: buffer b at columns 192 + 128*b
+constexpr unsigned kWorkHalfWarps = 2 * (kFusedThreads / 32 - 1);  // warps 1-15 gather / write back; warp 0 issues MMAs
 
 struct __align__(1024) Fused2Smem {
     unsigned char c[2][PIECES][GPIECE_BYTES];  // walker pieces (B operand), double-buffered
@@ -182,44 +183,50 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
         }
 
         // -------------------------------------------------- E(kk): |y|^2, log-density, accept test of tile kk (warps 0-3)
-        auto epilogue = [&](unsigned kk) {
+        auto epilogue = [&](unsigned kk) {  // warps 4-11
             const unsigned b = kk & 1, rb = kk % kRowBufs;
             const unsigned w0 = (blockIdx.x + kk * gridDim.x) * tr;
-            const int r = warp * 32 + lane;
-            double p0 = 0.0;  // current log-density: fetched while the GEMM may still be running
-            if ((unsigned)r < tr && w0 + r < W) p0 = p.lp[a0 + p.shard_begin + w0 + r];
+            const int ew = warp - 4;        // 0..7: warps 4-7 reduce columns [0,64), warps 8-11 columns [64,128)
+            const int quarter = warp & 3;   // the TMEM lane quarter this warp may read (output dimensions 32q .. 32q+31)
+            const int r = (ew & 3) * 32 + lane;  // the walker row of the accept test (warps 4-7)
+            double p0 = 0.0;  // current log-density: in flight while the squares are reduced
+            if (ew < 4 && (unsigned)r < tr && w0 + r < W) p0 = p.lp[a0 + p.shard_begin + w0 + r];
             mbar_wait(&sm.mma_done[b], (mph >> b) & 1u);
             __syncwarp();
             tc_fence_after();
-            const unsigned dbase = tmem + ((unsigned)(warp * 32) << 16) + kTmemD + b * BM;
-#pragma unroll 1
-            for (unsigned cb = 0; cb < tr; cb += 32) {
-                unsigned v[32];
-                tmem_ld32(dbase + cb, v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                float s[32];
+            const unsigned dbase = tmem + ((unsigned)(quarter * 32) << 16) + kTmemD + b * BM;
+            const unsigned cb0 = (unsigned)(ew >> 2) * 64u;
 #pragma unroll
-                for (int e = 0; e < 32; ++e) {
-                    const float y = cb + e < nwcols ? __uint_as_float(v[e]) : 0.0f;  // columns past the MMA's N are stale
-                    s[e] = y * y;
-                }
-                // transpose-and-add over the warp's 32 lanes (output dimensions): lane l ends with column cb + l
+            for (unsigned cc = 0; cc < 64; cc += 32) {
+                const unsigned cb = cb0 + cc;
+                if (cb < tr) {  // warp-uniform
+                    unsigned v[32];
+                    tmem_ld32(dbase + cb, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    float s[32];
 #pragma unroll
-                for (int hh = 16; hh >= 1; hh >>= 1) {
-                    const bool up = (lane & hh) != 0;
-#pragma unroll
-                    for (int e = 0; e < hh; ++e) {
-                        const float send = up ? s[e] : s[e + hh];
-                        const float keep = up ? s[e + hh] : s[e];
-                        s[e] = keep + __shfl_xor_sync(0xffffffffu, send, hh);
+                    for (int e = 0; e < 32; ++e) {
+                        const float y = cb + e < nwcols ? __uint_as_float(v[e]) : 0.0f;  // columns past the MMA's N are stale
+                        s[e] = y * y;
                     }
+                    // transpose-and-add over the warp's 32 lanes (output dimensions): lane l ends with column cb + l
+#pragma unroll
+                    for (int hh = 16; hh >= 1; hh >>= 1) {
+                        const bool up = (lane & hh) != 0;
+#pragma unroll
+                        for (int e = 0; e < hh; ++e) {
+                            const float send = up ? s[e] : s[e + hh];
+                            const float keep = up ? s[e + hh] : s[e];
+                            s[e] = keep + __shfl_xor_sync(0xffffffffu, send, hh);
+                        }
+                    }
+                    sm.part[quarter][cb + lane] = s[0];
                 }
-                sm.part[warp][cb + lane] = s[0];
             }
             tc_fence_before();
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // warps 0-3 only
+            asm volatile("bar.sync 1, 256;" ::: "memory");  // warps 4-11 only
             const unsigned w = w0 + r;
-            if ((unsigned)r < tr && w < W) {
+            if (ew < 4 && (unsigned)r < tr && w < W) {
                 const float ssf = ((sm.part[0][r] + sm.part[1][r]) + sm.part[2][r]) + sm.part[3][r];
                 const unsigned i = p.shard_begin + w;
                 const size_t k = a0 + i;
@@ -244,11 +251,11 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
         };
 
         // -------------------------------------------------- P3(kk): accepted rows (and the chain) of tile kk, all warps
-        auto writeback = [&](unsigned kk) {
+        auto writeback = [&](unsigned kk) {  // warps 1-15 (warp 0 only issues MMAs)
             const unsigned rb = kk % kRowBufs;
             const unsigned w0 = (blockIdx.x + kk * gridDim.x) * tr;
-            const unsigned nl = sm.nlist[rb];
-            for (unsigned l = warp * 2 + half16; l < nl; l += 2 * (kFusedThreads / 32)) {
+            const unsigned nl = warp == 0 ? 0u : sm.nlist[rb];
+            for (unsigned l = (warp - 1) * 2 + half16; l < nl; l += kWorkHalfWarps) {
                 const unsigned rr = sm.list[rb][l];
                 const bool accr = sm.acc[rb][rr] != 0;
                 const unsigned i = p.shard_begin + w0 + rr;
@@ -310,7 +317,7 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
                 if (tid == 8 * 32) sm.nlist[rb] = 0u;  // last used by tile k-3, whose P3 ended two barriers ago
                 // ---------------------------------------------- P1(k): proposals -> swizzled bf16 pieces c[b]  (as K2F)
                 {
-                    const unsigned hw = warp * 2 + half16;
+                    const unsigned hw = (warp - 1) * 2 + half16;  // 30 working half-warps: rows hw, hw+30, ... (warp 0 only issues MMAs)
                     auto row_live = [&](unsigned r) { return r < tr && w0 + r < W; };
                     auto row_load = [&](unsigned r, double2 (&xa)[4], double2 (&xb)[4]) {
                         const unsigned i = p.shard_begin + w0 + r;
@@ -353,16 +360,22 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
                             for (int pc = 0; pc < PIECES; ++pc) *reinterpret_cast<unsigned *>(sm.c[b][pc] + off) = pk[pc];
                         }
                     };
-                    double2 xa0[4], xb0[4], xa1[4], xb1[4];
-                    const bool l0 = row_live(hw), l1 = row_live(hw + 32), l2 = row_live(hw + 64), l3 = row_live(hw + 96);
-                    if (l0) row_load(hw, xa0, xb0);
-                    if (l1) row_load(hw + 32, xa1, xb1);
-                    if (l0) row_emit(hw, xa0, xb0);
-                    if (l2) row_load(hw + 64, xa0, xb0);
-                    if (l1) row_emit(hw + 32, xa1, xb1);
-                    if (l3) row_load(hw + 96, xa1, xb1);
-                    if (l2) row_emit(hw + 64, xa0, xb0);
-                    if (l3) row_emit(hw + 96, xa1, xb1);
+                    if (warp != 0) {
+                        double2 xa0[4], xb0[4], xa1[4], xb1[4];
+                        constexpr unsigned S = kWorkHalfWarps;
+                        const bool l0 = row_live(hw), l1 = row_live(hw + S), l2 = row_live(hw + 2 * S), l3 = row_live(hw + 3 * S),
+                                   l4 = row_live(hw + 4 * S);
+                        if (l0) row_load(hw, xa0, xb0);
+                        if (l1) row_load(hw + S, xa1, xb1);
+                        if (l0) row_emit(hw, xa0, xb0);
+                        if (l2) row_load(hw + 2 * S, xa0, xb0);
+                        if (l1) row_emit(hw + S, xa1, xb1);
+                        if (l3) row_load(hw + 3 * S, xa1, xb1);
+                        if (l2) row_emit(hw + 2 * S, xa0, xb0);
+                        if (l4) row_load(hw + 4 * S, xa0, xb0);
+                        if (l3) row_emit(hw + 3 * S, xa1, xb1);
+                        if (l4) row_emit(hw + 4 * S, xa0, xb0);
+                    }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> tensor-core proxy
                 __syncthreads();
@@ -394,11 +407,10 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
                 K2G_TICK(2);
             }
             if (k >= 1) {
-                if (warp < 4) {
+                if (warp >= 4 && warp < 12) {
                     epilogue(k - 1);
-                } else if (warp < 8) {  // the draws of tile k+1 while warps 0-3 reduce tile k-1
-                    if (k + 1 < T && k + 1 >= 2)
-                        tile_draws(h, blockIdx.x + (k + 1) * gridDim.x, (k + 1) % kRowBufs, (warp - 4) * 32 + lane);
+                } else if (warp >= 12) {  // the draws of tile k+1 while warps 4-11 reduce tile k-1
+                    if (k + 1 < T) tile_draws(h, blockIdx.x + (k + 1) * gridDim.x, (k + 1) % kRowBufs, (warp - 12) * 32 + lane);
                 }
                 mph ^= 1u << ((k - 1) & 1);
                 __syncthreads();

@@ -1,3 +1,4 @@
 #!/bin/bash
 mkdir -p gpurun_out
-KMC_TC=1 KMC_FUSED_VARIANT=2 KMC_LIB=$PWD/build/variants/libkmc_k2fprof.so timeout 60 python profiles/prof_run.py gaussian100d 200 0 > gpurun_out/k2g_phase_cycles.log 2>&1; tail -4 gpurun_out/k2g_phase_cycles.log
+timeout 60 python -m pytest tests -m gpu -x -q > gpurun_out/final2_pytest.log 2>&1; echo "pytest exit $?" >> gpurun_out/final2_pytest.log; tail -4 gpurun_out/final2_pytest.log
+timeout 40 python bench.py --workload gaussian100d --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/final2_bench_gaussian100d.json 2> gpurun_out/final2_bench_gaussian100d.err; cut -c1-200 gpurun_out/final2_bench_gaussian100d.json

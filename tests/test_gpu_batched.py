@@ -229,6 +229,7 @@ def test_gaussian_fused_kernel_equals_three_kernel_pipeline(km):
         prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 3))
         ld = km.LogDensity("gaussian", d, prm)
         ld.set_option("tensor_cores", 1)
+        ld.set_option("fused_variant", 1)          # K2F; the default K2G sums |y|^2 in a different order
         x0 = np.linspace(-1, 1, d) + cases.ball(np.zeros(d), 0.7, nw, 5)
         out = []
         for mode in (0, 1):
