@@ -86,8 +86,12 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                            kmc_density_t *out);
 int32_t kmc_density_destroy(kmc_density_t h);
 /* Options: "tensor_cores" = 0/1 (logistic with d = 32 and bf16-representable data runs its
- * walkers x data logits GEMM on tcgen05 tensor cores by default; 0 forces the FP64 kernel).
- * Info keys: "tensor_cores" (1 if the tcgen05 path will be used), "batched". */
+ * walkers x data logits GEMM on tcgen05 tensor cores by default; 0 forces the FP64 kernel; the
+ * dense Gaussian with 16 < d <= 128 is exact FP64 by default and opts in with 1).
+ * "fused_variant" = 2/1: which fused persistent kernel the tensor-core dense Gaussian uses in
+ * launch_mode 0 -- 2 (default): matrix pieces resident in TMEM; 1: matrix pieces in shared memory
+ * (bit-identical to the three-kernel pipeline of launch_mode 1).
+ * Info keys: "tensor_cores" (1 if the tcgen05 path will be used), "batched", "fused_variant". */
 int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value);
 int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value);
 /* Batched log-density of nw points (host in, host out).  Used for the initial p0s
