@@ -19,7 +19,7 @@
 //       warp 1     MMA issuer: one elected thread, 6 x tcgen05.mma.cta_group::1.kind::f16
 //                  (M=128, N=256, K=16) per tile = 3 pieces x 2 k-steps, lo piece first;
 //                  tcgen05.commit frees the smem stage and publishes the accumulator
-//       warps 2-9  epilogue: tcgen05.ld 32x32b.x32 from the double-buffered TMEM accumulator
+//       warps 2-17 epilogue: tcgen05.ld 32x32b.x32 from the double-buffered TMEM accumulator
 //                  (2 x 256 columns = all 512); per logit one MUFU ex2, one FFMA (running product of
 //                  1 + 2^-|s'|, one lg2 per 32 columns) and one FADD (sum of |s'|); FP32 partial
 //                  per 32 columns, FP64 running sum per row, tail columns masked
