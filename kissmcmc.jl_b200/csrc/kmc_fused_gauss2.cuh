@@ -362,19 +362,31 @@ gaussian_fused2_kernel(const RunParams p, const Fused2Params fp) {
                     };
                     if (warp != 0) {
                         double2 xa0[4], xb0[4], xa1[4], xb1[4];
+#ifdef KMC_K2G_ROWMAP4
+                        // Rows of the two half-warps of a warp differ by 4: with the 128-byte swizzle their 64-byte store
+                        // groups then fall into complementary halves of the 32 banks (rows r and r+1 share a half three
+                        // times out of four: 2-way conflicts on the STS.32 of the piece stores).  Slot m of warp w' is
+                        // n = w' + 15 m -> row 8 (n / 4) + n % 4 + 4 * (half-warp); every row < 152 exactly once.
+                        auto slot_row = [&](unsigned m) {
+                            const unsigned nn = (unsigned)(warp - 1) + 15u * m;
+                            return 8u * (nn >> 2) + (nn & 3u) + 4u * half16;
+                        };
+                        const unsigned r0 = slot_row(0), r1 = slot_row(1), r2 = slot_row(2), r3 = slot_row(3), r4 = slot_row(4);
+#else
                         constexpr unsigned S = kWorkHalfWarps;
-                        const bool l0 = row_live(hw), l1 = row_live(hw + S), l2 = row_live(hw + 2 * S), l3 = row_live(hw + 3 * S),
-                                   l4 = row_live(hw + 4 * S);
-                        if (l0) row_load(hw, xa0, xb0);
-                        if (l1) row_load(hw + S, xa1, xb1);
-                        if (l0) row_emit(hw, xa0, xb0);
-                        if (l2) row_load(hw + 2 * S, xa0, xb0);
-                        if (l1) row_emit(hw + S, xa1, xb1);
-                        if (l3) row_load(hw + 3 * S, xa1, xb1);
-                        if (l2) row_emit(hw + 2 * S, xa0, xb0);
-                        if (l4) row_load(hw + 4 * S, xa0, xb0);
-                        if (l3) row_emit(hw + 3 * S, xa1, xb1);
-                        if (l4) row_emit(hw + 4 * S, xa0, xb0);
+                        const unsigned r0 = hw, r1 = hw + S, r2 = hw + 2 * S, r3 = hw + 3 * S, r4 = hw + 4 * S;
+#endif
+                        const bool l0 = row_live(r0), l1 = row_live(r1), l2 = row_live(r2), l3 = row_live(r3), l4 = row_live(r4);
+                        if (l0) row_load(r0, xa0, xb0);
+                        if (l1) row_load(r1, xa1, xb1);
+                        if (l0) row_emit(r0, xa0, xb0);
+                        if (l2) row_load(r2, xa0, xb0);
+                        if (l1) row_emit(r1, xa1, xb1);
+                        if (l3) row_load(r3, xa1, xb1);
+                        if (l2) row_emit(r2, xa0, xb0);
+                        if (l4) row_load(r4, xa0, xb0);
+                        if (l3) row_emit(r3, xa1, xb1);
+                        if (l4) row_emit(r4, xa0, xb0);
                     }
                 }
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic smem writes -> tensor-core proxy
