@@ -112,3 +112,29 @@ def test_lane_butterfly_leaves_column_l_in_lane_l():
         s = new
         hh >>= 1
     assert np.array_equal(s[:, 0], v.sum(axis=0))
+
+
+def test_balanced_tiling_of_the_fused_gaussian_kernels_covers_every_walker_once():
+    """K2F / K2G tile the active half as `waves` tiles per CTA of `tr <= 128` walkers (kmc_fused_gauss*.cuh); the host
+    launches min(ceil(W / 128), SMs) CTAs (kmc_api.cu).  Emulated for many sizes: every walker position belongs to exactly
+    one (CTA, tile), no CTA gets more than `waves` tiles, and the MMA's N (tr rounded up to 16) stays legal."""
+    for src in (FUSED, (CSRC / "kmc_fused_gauss2.cuh").read_text()):
+        assert "const unsigned waves = ((W + BM - 1) / BM + gridDim.x - 1) / gridDim.x;" in src
+        assert "(W + waves * gridDim.x - 1) / (waves * gridDim.x)" in src
+    BM, nsm = 128, 148
+    sizes = list(range(1, 700)) + [1000, 2 ** 15, 148 * 128, 148 * 128 + 1, 148 * 128 * 2 + 777, 148 * 128 * 3 - 50, 10 ** 6 + 3]
+    for W in sizes:
+        grid = min((W + BM - 1) // BM, nsm)
+        waves = ((W + BM - 1) // BM + grid - 1) // grid
+        tr = min(BM, (W + waves * grid - 1) // (waves * grid))
+        ntiles = (W + tr - 1) // tr
+        assert 1 <= tr <= BM and 16 <= ((tr + 15) & ~15) <= 128
+        covered = 0
+        for cta in range(grid):
+            T = (ntiles - cta + grid - 1) // grid if ntiles > cta else 0
+            assert T <= waves
+            for k in range(T):
+                w0 = (cta + k * grid) * tr
+                covered += max(0, min(tr, W - w0))
+        assert covered == W, (W, grid, waves, tr, ntiles)
+        assert (ntiles - 1) * tr < W <= ntiles * tr
