@@ -76,6 +76,32 @@ def dominant_kernel(wl, tensor, launch_mode):
     return "emcee_run_kernel"
 
 
+def gaussian_params(mean, cov):
+    """[mu, A row-major, lognorm], A = chol(cov^-1)^T: logp = lognorm - |A (x - mu)|^2 / 2 (include/kissmcmc_cuda.h)."""
+    mu = np.atleast_1d(np.asarray(mean, dtype=np.float64))
+    prec = np.linalg.inv(np.atleast_2d(np.asarray(cov, dtype=np.float64)))
+    L = np.linalg.cholesky((prec + prec.T) / 2)
+    lognorm = float(np.sum(np.log(np.diag(L))) - 0.5 * mu.size * np.log(2 * np.pi))
+    return np.concatenate([mu, L.T.ravel(), [lognorm]])
+
+
+def spd_cov(d, seed=0):
+    """Sigma = A A^T / d + I, stated seed."""
+    a = np.random.default_rng(seed).standard_normal((d, d))
+    return a @ a.T / d + np.eye(d)
+
+
+def logistic_problem(N, d, seed=0):
+    """Synthetic Bayesian logistic regression: X ~ N(0,1) rounded to
+    bf16-representable values, theta* ~ N(0,1)/sqrt(d), y ~ Bernoulli(sigmoid(X theta*))."""
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, d)).astype(np.float32)
+    X = (X.view(np.uint32) & np.uint32(0xFFFF0000)).view(np.float32)
+    tstar = rng.standard_normal(d) / np.sqrt(d)
+    y = (rng.random(N) < 1.0 / (1.0 + np.exp(-(X.astype(np.float64) @ tstar)))).astype(np.float32)
+    return X, y, tstar
+
+
 def make_inputs(wl, seed):
     rng = np.random.default_rng(seed)
     d, nw = wl["d"], wl["nw"]
@@ -83,12 +109,10 @@ def make_inputs(wl, seed):
         params = [1.0, 100.0, 20.0]
         x0 = 0.1 * rng.standard_normal((nw, d))
     elif wl["plugin"] == "gaussian":
-        from tests import cases
-        params = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 1))
+        params = gaussian_params(np.linspace(-1, 1, d), spd_cov(d, 1))
         x0 = 0.1 * rng.standard_normal((nw, d))
     elif wl["plugin"] == "logistic":
-        from tests import cases
-        X, y, tstar = cases.logistic_problem(N=wl["ndata"], d=d, seed=seed)
+        X, y, tstar = logistic_problem(N=wl["ndata"], d=d, seed=seed)
         wl["_data"] = np.concatenate([X.ravel(), y])
         params = [10.0]
         x0 = tstar + 1e-3 * rng.standard_normal((nw, d))
@@ -239,87 +263,164 @@ def cpu_baseline(wl, seconds=15.0):
                       f"(of {wl['niter_walker']}), {dt:.1f} s, C restatement of the reference loop with OpenMP"}
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="rosenbrock2d", choices=sorted(WORKLOADS))
-    ap.add_argument("--launch-mode", type=int, default=0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--tensor-cores", type=int, default=None, choices=[0, 1],
-                    help="force the tcgen05 (1) or FP64 (0) log-density kernel of the dense plugins")
-    args = ap.parse_args()
-    wl = WORKLOADS[args.workload]
-    if args.impl == "reference":
-        return run_reference(args, wl)
+def roofline_of(wl, workload, tensor, launch_mode, k_ms, traffic):
+    """The roofline object of the dominant kernel of one step of `workload`."""
+    d, nw, nitw, nthin = wl["d"], wl["nw"], wl["niter_walker"], wl["nthin"]
+    ns = (nitw - nitw // 2) // nthin
+    walker_steps = nw * nitw
+    peaks_path = ROOT / "MEASURED_PEAKS.json"
+    peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
+    if wl["plugin"] == "logistic":      # tensor-bound nominally: 2*d*N flops per walker-step
+        tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
+        flops = 2.0 * d * wl["ndata"] * walker_steps
+        tflops = flops / (k_ms * 1e-3) / 1e12
+        return {"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
+                "traffic": traffic, "kernel": "tc::logistic_tc_kernel" if tensor else "logistic_logp_kernel",
+                "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
+                "algorithmic_flops_per_step": flops, "kernel_ms_per_step": k_ms,
+                "note": "algorithmic flops 2*d*N per walker-step; the tcgen05 kernel issues 3x that (theta split into 3 "
+                        "bf16 pieces) and is bounded by its softplus epilogue"}
+    peak = peaks.get("hbm_gbs", 6650.0)
+    alg = b_step(d) * walker_steps + (8 * d + 8) * nw * ns
+    achieved = alg / (k_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": traffic, "kernel": dominant_kernel(wl, tensor, launch_mode),
+            "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback (B200_PROFILING.md)",
+            "algorithmic_bytes_per_launch": alg, "kernel_ms_per_launch": k_ms,
+            "note": "algorithmic bytes = (24d+24) per walker-step + (8d+8) per stored sample; a state that fits L2 / "
+                    "shared memory makes frac against the HBM copy peak able to exceed 1"}
 
-    import torch
-    import torch.distributed as dist
 
+def measure_traffic(workload, kernel_regex, timeout=240):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE bench-size launch of the dominant kernel, measured now:
+    ncu around a child process that runs one step of the same workload with the same library build.  Returns
+    (bytes | None, how)."""
+    import hashlib
+    import shutil
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not Path(ncu).exists():
+        return None, "ncu not found"
     import kissmcmc_b200 as km
+    sha = hashlib.sha256(Path(km.LIB_PATH).read_bytes()).hexdigest()[:16]
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+           f"regex:{kernel_regex}", "-c", "1", "--csv", sys.executable, str(ROOT / "bench.py"), "--traffic-child",
+           "--workload", workload]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+    except Exception as e:      # noqa: BLE001
+        return None, f"ncu failed: {e!r}"
+    tot, seen = 0.0, 0
+    import csv
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    for row in csv.reader(r.stdout.splitlines()):
+        if len(row) > 3 and row[-3] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            try:
+                tot += float(row[-1].replace(",", "")) * scale.get(row[-2], 1.0)
+                seen += 1
+            except ValueError:
+                pass
+    if seen != 2:
+        return None, "ncu gave no dram counters (rc %d): %s" % (r.returncode, (r.stdout + r.stderr)[-200:].replace("\n", " "))
+    return tot, f"ncu dram__bytes_read.sum+dram__bytes_write.sum of one {kernel_regex} launch, library sha256 {sha}"
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+def traffic_child(wl_name):
+    """One step of the workload (run under ncu by measure_traffic)."""
+    import kissmcmc_b200 as km
+    wl = WORKLOADS[wl_name]
+    params, x0 = make_inputs(wl, 1000)
+    ld = km.LogDensity(wl["plugin"], wl["d"], params, data=wl.get("_data"))
+    if wl["plugin"] == "logistic" or (wl["plugin"] == "gaussian" and wl["d"] > 16):
+        ld.set_option("tensor_cores", 1)
+    s = km.Sampler(ld, x0, wl["niter_walker"], wl["niter_walker"] // 2, wl["nthin"], 2.0, seed=1)
+    s.run(-1)
+    s.close()
+    return 0
 
+
+class Env:
+    """Process-wide plumbing of one bench process (one rank)."""
+
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise RuntimeError("bench.py needs a CUDA device; there is no CPU fallback")
+        torch.cuda.set_device(self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
+        self.stream = torch.cuda.Stream()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_sum(self, vals):
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        if self.world == 1:
+            return vals, vals
+        mx, sm = t.clone(), t.clone()
+        self.dist.all_reduce(mx, op=self.dist.ReduceOp.MAX)
+        self.dist.all_reduce(sm, op=self.dist.ReduceOp.SUM)
+        return mx.tolist(), sm.tolist()
+
+
+def run_workload(env, km, workload, steps, warmup, launch_mode=0, tensor_cores=None, e2e_steps=3):
+    """Times `steps` steps (complete emcee jobs) of one workload on every rank (independent ensembles).
+    Returns the pieces of a bench line: value / ms_per_step / roofline / e2e / clocks / launches."""
+    torch = env.torch
+    wl = WORKLOADS[workload]
+    rank, world, local = env.rank, env.world, env.local
     d, nw, nitw, nthin = wl["d"], wl["nw"], wl["niter_walker"], wl["nthin"]
     nbw = nitw // 2
     ns = (nitw - nbw) // nthin
     params, x0 = make_inputs(wl, 1000 + rank)
     ld = km.LogDensity(wl["plugin"], d, params, data=wl.get("_data"), device=local)
-    if args.tensor_cores is not None:
-        ld.set_option("tensor_cores", args.tensor_cores)
-    elif wl["plugin"] == "gaussian" and d > 16:
-        ld.set_option("tensor_cores", 1)          # bench default for configs[2]: the tcgen05 Mahalanobis GEMM
+    if tensor_cores is not None:
+        ld.set_option("tensor_cores", tensor_cores)
+    elif wl["plugin"] == "logistic" or (wl["plugin"] == "gaussian" and d > 16):
+        ld.set_option("tensor_cores", 1)          # bench default for configs[2], configs[3]: the tcgen05 kernels (opt-in)
     tensor = ld.info("tensor_cores") == 1.0
-    stream = torch.cuda.Stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    stream, flush = env.stream, env.flush
 
     def new_sampler(step):
         # independent ensembles: rank-distinct Philox key and walker-id range
         s = km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, seed=(step << 8) | rank, walker_id_base=rank * nw,
-                       launch_mode=args.launch_mode)
+                       launch_mode=launch_mode)
         s.set_stream(stream.cuda_stream)
         return s
 
     walker_steps_per_step = nw * nitw
-    alg_bytes_per_step = b_step(d) * nw * nitw + (8 * d + 8) * nw * ns
 
     # ---- value: device-timed, inputs resident in HBM -------------------------------------
-    total = args.warmup + args.steps
+    total = warmup + steps
     samplers = [new_sampler(i) for i in range(total)]
     with torch.cuda.stream(stream):
-        for i in range(args.warmup):
+        for i in range(warmup):
             flush.fill_(i & 0xFF)
             samplers[i].run(-1, sync=False)
-    barrier()
+    env.barrier()
     clocks = ClockSampler(local)
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    env.barrier()
     with torch.cuda.stream(stream):
         ev0.record(stream)
-        for i in range(args.warmup, total):
+        for i in range(warmup, total):
             flush.fill_(i & 0xFF)                     # L2 flush between steps (inside the timed region)
             samplers[i].run(-1, sync=False)
         ev1.record(stream)
-    barrier()
+    env.barrier()
     clk = clocks.stop()
     dev_ms = ev0.elapsed_time(ev1)
     kern_ms, launches = [], 0
-    for i in range(args.warmup, total):
+    for i in range(warmup, total):
         ms, n = samplers[i].last_run_ms()
         kern_ms.append(ms)
         launches += n
@@ -335,7 +436,7 @@ def main():
     def e2e_step(step):
         ta = time.perf_counter()
         s = km.Sampler(ld, x0_pinned.numpy(), nitw, nbw, nthin, 2.0, seed=(step << 8) | rank,
-                       walker_id_base=rank * nw, launch_mode=args.launch_mode)
+                       walker_id_base=rank * nw, launch_mode=launch_mode)
         tb = time.perf_counter()
         s.run(-1)
         tc = time.perf_counter()
@@ -346,87 +447,206 @@ def main():
             print(f"e2e step {step}: create {1e3 * (tb - ta):.1f} run {1e3 * (tc - tb):.1f} results "
                   f"{1e3 * (td - tc):.1f} close {1e3 * (time.perf_counter() - td):.1f} ms", file=sys.stderr)
 
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, min(steps, e2e_steps))
     e2e_step(0)
-    barrier()
+    env.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(100 + i)
-    barrier()
+    env.barrier()
     e2e_s = time.perf_counter() - t0
+    del x0_pinned, out_th, out_lp, out_ar
+    km.lib.kmc_trim()                             # give the cached device blocks back before the next workload
 
-    t = torch.tensor([dev_ms, e2e_s * 1e3, max(kern_ms), float(launches)], dtype=torch.float64, device="cuda")
+    (dev_ms, e2e_ms, _, _), (_, _, _, launches) = env.max_sum([dev_ms, e2e_s * 1e3, max(kern_ms), float(launches)])
+    k_ms = statistics.mean(kern_ms)
+    return {
+        "wl": wl, "tensor": tensor, "k_ms": k_ms,
+        "value": world * walker_steps_per_step * steps / (dev_ms * 1e-3),
+        "ms_per_step": dev_ms / steps,
+        "dtype": "bf16x3 split operands, f32 accumulate (tcgen05); f64 state" if tensor else "f64",
+        "e2e": {"value": world * walker_steps_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
+                "h2d_bytes_per_step": int(x0.nbytes), "d2h_bytes_per_step": int(nw * ns * d * 8 + nw * ns * 8 + nw * 4),
+                "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
+        "gpu_launches": int(launches), "clocks": clk,
+        "config": {
+            "workload": workload, "tensor_cores": tensor, "description": wl["desc"], "plugin": wl["plugin"], "d": d,
+            "nwalkers_per_gpu": nw, "niter_walker": nitw, "nburnin_walker": nbw, "nthin": nthin,
+            "samples_per_walker": ns, "a_scale": 2.0, "rng": "philox4x32-10",
+            "parallelism": "1 ensemble" if world == 1 else f"{world} independent ensembles (no collective)",
+            "launch_mode": "persistent kernel, grid barrier per half-step" if launch_mode == 0
+            else "one launch per half-step",
+            "l2": "ensemble state is L2-resident by construction across the dependent half-steps of one step; "
+                  "L2 flushed (256 MiB fill) between steps, inside the timed region",
+        },
+    }
+
+
+def sharded_section(env, km, lg_nw=24, iters=20, warm=4):
+    """BASELINE.json configs[4]: ONE 2^24-walker 10-D Gaussian ensemble sharded by walker index over all ranks.
+    Rank 0 first times the unsharded ensemble on its GPU (the in-run 1-GPU anchor); then all ranks time the push
+    exchange (csrc/kmc_push.cuh: owner-computes packed row pushes over NVLink, no collective) and the NCCL
+    all-gather exchange north_star names.  Device time = max over ranks of each rank's CUDA-event time of its own
+    kernels (all-gather: events around kernels + collectives on the one stream they share).  Strong scaling: the
+    ensemble is fixed; `weak` repeats it with 2^21 walkers per GPU."""
+    torch, dist = env.torch, env.dist
+    rank, world, local = env.rank, env.world, env.local
+    from kissmcmc_b200 import distributed as kd
+
+    def one(nw, with_allgather):
+        wl = dict(WORKLOADS["gaussian10d"], nw=nw)
+        params, x0 = make_inputs(wl, 1)              # the same ensemble on every rank
+        d, nhalf = wl["d"], nw // 2
+        ld = km.LogDensity("gaussian", d, params, device=local)
+        out = {"nwalkers": nw, "d": d, "iters": iters}
+        ms1 = 0.0
+        if rank == 0:                                 # 1-GPU anchor: the unsharded ensemble on this rank's GPU
+            s = km.Sampler(ld, x0, iters + warm, 0, 10**6, 2.0, 7, device=local)
+            s.run(warm)
+            s.run(iters)
+            ms1, _ = s.last_run_ms()
+            s.close()
+            km.lib.kmc_trim()
+        env.barrier()
+        (ms1,), _ = env.max_sum([ms1])
+        out["value_1gpu"] = nw * iters / (ms1 * 1e-3)
+        out["ms_per_halfstep_1gpu"] = ms1 / (2 * iters)
+        if world == 1:
+            return out
+        begin, count = kd.shard_range(nw, rank, world)
+        # ---- push exchange: one persistent kernel per rank
+        s = km.Sampler(ld, x0, iters + warm, 0, 10**6, 2.0, 7, device=local, shard=(begin, count),
+                       exchange=km.EXCHANGE_PUSH)
+        allh = [None] * world
+        dist.all_gather_object(allh, s.window_export())
+        s.window_attach(allh, rank)
+        env.barrier()
+        s.run(warm, sync=True)
+        env.barrier()
+        s.run(iters, sync=True)
+        ms, _ = s.last_run_ms()
+        env.barrier()
+        s.close()
+        (msp,), _ = env.max_sum([ms])
+        out["value_push"] = nw * iters / (msp * 1e-3)
+        out["ms_per_halfstep_push"] = msp / (2 * iters)
+        out["efficiency_push"] = out["value_push"] / (world * out["value_1gpu"])
+        out["bytes_nvlink_per_halfstep"] = count * 8 * d * (world - 1) // world       # per GPU, each direction
+        out["nvlink_gbs_per_gpu"] = out["bytes_nvlink_per_halfstep"] / (msp / (2 * iters) * 1e-3) / 1e9
+        if not with_allgather:
+            return out
+        # ---- NCCL all-gather of the updated half after every half-step (every rank holds the full ensemble)
+        km.lib.kmc_trim()
+        s = km.Sampler(ld, x0, iters + warm, 0, 10**6, 2.0, 7, device=local, launch_mode=1, shard=(begin, count))
+        st = torch.cuda.Stream()
+        s.set_stream(st.cuda_stream)
+        xt = kd.x_tensor(s)
+
+        def halfsteps(n, h0):
+            for h in range(h0, h0 + n):
+                s.run_half(1)
+                half = xt[(h & 1) * nhalf:((h & 1) + 1) * nhalf]
+                dist.all_gather_into_tensor(half.view(-1), half[begin:begin + count].reshape(-1))
+        with torch.cuda.stream(st):
+            halfsteps(2 * warm, 0)
+            env.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st)
+            halfsteps(2 * iters, 2 * warm)
+            e1.record(st)
+            env.barrier()
+        (msa,), _ = env.max_sum([e0.elapsed_time(e1)])
+        s.close()
+        km.lib.kmc_trim()
+        out["value_allgather"] = nw * iters / (msa * 1e-3)
+        out["ms_per_halfstep_allgather"] = msa / (2 * iters)
+        out["allgather_bytes_per_rank_per_halfstep"] = nhalf * d * 8
+        return out
+
+    res = one(1 << lg_nw, True)
+    res["workload"] = f"gaussian10d, ONE ensemble of 2^{lg_nw} walkers sharded by walker index (strong scaling)"
     if world > 1:
-        mx = t.clone()
-        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-        sm = t.clone()
-        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms, e2e_ms, launches = mx[0].item(), mx[1].item(), int(sm[3].item())
-    else:
-        e2e_ms = e2e_s * 1e3
+        res["value_peer"] = res["value_push"]         # the fused peer-memory path is the push exchange
+        res["efficiency_peer"] = res["efficiency_push"]
+        weak = one((1 << 21) * world, False)
+        anchor = one(1 << 21, False) if world > 1 else weak
+        res["weak"] = {"nwalkers_per_gpu": 1 << 21, "value_1gpu_one_shard": anchor["value_1gpu"],
+                       "value_push": weak.get("value_push"),
+                       "efficiency": weak["value_push"] / (world * anchor["value_1gpu"]),
+                       "ms_per_halfstep_push": weak.get("ms_per_halfstep_push"),
+                       "ms_per_halfstep_1gpu_one_shard": anchor["ms_per_halfstep_1gpu"]}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="rosenbrock2d", choices=sorted(WORKLOADS))
+    ap.add_argument("--launch-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the short lines of the other four configs (N=1)")
+    ap.add_argument("--no-sharded", action="store_true", help="skip the sharded-ensemble section")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu DRAM-traffic measurement (N=1)")
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--tensor-cores", type=int, default=None, choices=[0, 1],
+                    help="force the tcgen05 (1) or FP64 (0) log-density kernel of the dense plugins")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, wl)
+    if args.traffic_child:
+        return traffic_child(args.workload)
+
+    import kissmcmc_b200 as km
+    env = Env()
+    rank, world = env.rank, env.world
+
+    r = run_workload(env, km, args.workload, args.steps, args.warmup, args.launch_mode, args.tensor_cores)
+    default_run = args.workload == "rosenbrock2d" and args.launch_mode == 0 and args.tensor_cores is None
+
+    others = []
+    if world == 1 and default_run and not args.no_others:      # the other four configs, short, on the same box
+        for name in ("exponential1d", "gaussian100d", "logistic32d", "gaussian10d"):
+            o = run_workload(env, km, name, 3, 3, 0, None, e2e_steps=2)
+            others.append({"workload": name, "value": o["value"], "unit": UNIT, "steps": 3, "warmup": 3,
+                           "ms_per_step": o["ms_per_step"], "dtype": o["dtype"],
+                           "roofline": roofline_of(o["wl"], name, o["tensor"], 0, o["k_ms"], None),
+                           "e2e": o["e2e"], "clocks": o["clocks"], "gpu_launches": o["gpu_launches"],
+                           "description": o["wl"]["desc"]})
+
+    sharded = None
+    if default_run and not args.no_sharded:
+        sharded = sharded_section(env, km)
+
+    traffic, traffic_how = None, "not measured"
+    if rank == 0 and world == 1 and not args.no_traffic:
+        env.torch.cuda.synchronize()
+        kern = dominant_kernel(r["wl"], r["tensor"], args.launch_mode).split("::")[-1].split(" ")[0]
+        traffic, traffic_how = measure_traffic(args.workload, kern)
 
     if rank == 0:
-        peaks_path = ROOT / "MEASURED_PEAKS.json"
-        if peaks_path.exists():
-            peak, peak_src = json.loads(peaks_path.read_text())["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
-        else:
-            peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        k_ms = statistics.mean(kern_ms)
-        achieved = alg_bytes_per_step / (k_ms * 1e-3) / 1e9
-        traffic = None
-        tpath = ROOT / "profiles" / "traffic.json"
-        if tpath.exists():
-            traffic = json.loads(tpath.read_text()).get(args.workload)
-        if wl["plugin"] == "logistic":      # tensor-bound nominally: 2*d*N flops per walker-step
-            peaks = json.loads(peaks_path.read_text()) if peaks_path.exists() else {}
-            tpeak = peaks.get("bf16_tflops_sustained", 1400.0)
-            tflops = 2.0 * d * wl["ndata"] * walker_steps_per_step / (k_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "achieved": tflops, "peak": tpeak, "unit": "TFLOP/s", "frac": tflops / tpeak,
-                    "traffic": traffic, "kernel": "tc::logistic_tc_kernel" if tensor else "logistic_logp_kernel",
-                    "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback",
-                    "algorithmic_flops_per_step": 2.0 * d * wl["ndata"] * walker_steps_per_step,
-                    "kernel_ms_per_step": k_ms,
-                    "note": "algorithmic flops 2*d*N per walker-step; the tcgen05 kernel issues 3x that (theta split "
-                            "into 3 bf16 pieces) and is bounded by the MUFU softplus epilogue (profiles/r1_summary.md)"}
-        else:
-            roof = None
+        roof = roofline_of(r["wl"], args.workload, r["tensor"], args.launch_mode, r["k_ms"], traffic)
+        roof["traffic_source"] = traffic_how
         line = {
-            "metric": METRIC, "value": world * walker_steps_per_step * args.steps / (dev_ms * 1e-3), "unit": UNIT,
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3 split operands, f32 accumulate (tcgen05); f64 state" if tensor else "f64",
-            "data": "synthetic",
-            "config": {
-                "workload": args.workload, "tensor_cores": tensor, "description": wl["desc"], "plugin": wl["plugin"], "d": d,
-                "nwalkers_per_gpu": nw, "niter_walker": nitw, "nburnin_walker": nbw, "nthin": nthin,
-                "samples_per_walker": ns, "a_scale": 2.0, "rng": "philox4x32-10",
-                "parallelism": "1 ensemble" if world == 1 else f"{world} independent ensembles (no collective)",
-                "launch_mode": "persistent kernel, grid barrier per half-step" if args.launch_mode == 0
-                else "one launch per half-step",
-                "l2": "ensemble state is L2-resident by construction across the dependent half-steps of one step; "
-                      "L2 flushed (256 MiB fill) between steps, inside the timed region",
-            },
-            "roofline": roof or {
-                "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": dominant_kernel(wl, tensor, args.launch_mode),
-                "algorithmic_bytes_per_launch": alg_bytes_per_step, "kernel_ms_per_launch": k_ms,
-                "note": "algorithmic bytes = (24d+24) per walker-step + (8d+8) per stored sample; a state that fits "
-                        "L2 / shared memory makes frac against the HBM copy peak able to exceed 1",
-            },
-            "e2e": {"value": world * walker_steps_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT,
-                    "h2d_bytes_per_step": int(x0.nbytes),
-                    "d2h_bytes_per_step": int(out_th.numel() * 8 + out_lp.numel() * 8 + nw * 4),
-                    "steps": e2e_steps, "ms_per_step": e2e_ms / e2e_steps},
-            "gpu_launches": launches,
-            "clocks": clk,
+            "metric": METRIC, "value": r["value"], "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": r["dtype"],
+            "data": "synthetic", "config": r["config"], "roofline": roof, "e2e": r["e2e"],
+            "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
         }
+        if others:
+            line["others"] = others
+        if sharded:
+            line["sharded"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(wl)
         print(json.dumps(line))
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        env.dist.barrier()
+        env.dist.destroy_process_group()
     return 0
 
 

@@ -41,8 +41,19 @@ extern "C" {
 #define KMC_MODE_PHILOX 0 /* free-running, counter-based Philox4x32-10 draws */
 #define KMC_MODE_REPLAY 1 /* partner / z / u uploaded by the caller */
 
+/* How the shards of one ensemble see each other's rows (kmc_emcee_opts.exchange, sharded samplers only). */
+#define KMC_EXCHANGE_REPLICA 0 /* every shard holds the FULL ensemble's positions; the caller exchanges the updated
+                                  half between half-steps (all-gather), or the legacy pull mode (kmc_emcee_set_peers) */
+#define KMC_EXCHANGE_PUSH 1    /* every shard holds ONLY its rows plus a receive ring; the owners of the passive half
+                                  push the partner rows every peer will ask for (kmc_emcee_window_*, kmc_multi_*) */
+
+/* kmc_emcee_create_multi modes */
+#define KMC_MULTI_SHARDED 0     /* ONE ensemble sharded by walker index over the devices (push exchange) */
+#define KMC_MULTI_INDEPENDENT 1 /* one independent ensemble per device, no communication */
+
 typedef struct kmc_density_s *kmc_density_t;
 typedef struct kmc_sampler_s *kmc_sampler_t;
+typedef struct kmc_multi_s *kmc_multi_t;
 
 typedef struct kmc_emcee_opts {
     int64_t niter_walker;   /* niter / nwalkers    (src/samplers.jl:203) */
@@ -56,7 +67,7 @@ typedef struct kmc_emcee_opts {
                                one ensemble (or independent ensembles) draw distinct streams */
     int32_t launch_mode;    /* 0 = persistent kernel, grid barrier between half-steps (default);
                                1 = one launch per half-step */
-    int32_t reserved;
+    int32_t exchange;       /* KMC_EXCHANGE_* (sharded samplers; 0 otherwise) */
     /* Sharded ensemble (one ensemble over several GPUs): this sampler holds
      * the FULL ensemble's positions but updates only positions [shard_begin, shard_begin +
      * shard_count) of each half; the caller makes the updated slices of the other shards visible
@@ -64,6 +75,13 @@ typedef struct kmc_emcee_opts {
      * keyed by the global walker index, so a sharded run reproduces the single-GPU run exactly. */
     int64_t shard_begin;
     int64_t shard_count;
+    /* KMC_EXCHANGE_PUSH tuning; 0 = the library's choice.  push_chunk: walkers per chunk (the unit of the "rows have
+     * landed" flags; <= 1024; default 128 * ranks), push_cap: rows per receive-ring slot (<= 256; rows past it are read
+     * from the owner directly; default 192), push_lag: chunks by which the updates trail the pushes. */
+    int32_t push_chunk;
+    int32_t push_cap;
+    int32_t push_lag;
+    int32_t reserved;
 } kmc_emcee_opts;
 
 /* Library / device ------------------------------------------------------------------- */
@@ -130,6 +148,14 @@ int32_t kmc_emcee_sync(kmc_sampler_t s);
 int32_t kmc_emcee_ipc_export(kmc_sampler_t s, void *handle_x, void *handle_flags);
 int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *handles_flags, int32_t nranks,
                             int32_t rank);
+/* Push mode (KMC_EXCHANGE_PUSH; csrc/kmc_push.cuh), one process per GPU: the sampler's positions, receive ring and
+ * chunk flags live in ONE device allocation (the "window").  kmc_emcee_window_export writes its 64-byte CUDA IPC
+ * handle; the caller exchanges the handles and passes all ranks' handles, rank-major, to kmc_emcee_window_attach.
+ * Then every rank calls kmc_emcee_run concurrently: no collective, no cross-GPU barrier -- the owners of the passive
+ * half push packed partner rows over NVLink and every consumer starts as soon as its chunk's rows have landed.
+ * Replaces, across GPUs, the shared-memory read of the passive half at src/samplers.jl:255 (sweep :246-273). */
+int32_t kmc_emcee_window_export(kmc_sampler_t s, void *handle);
+int32_t kmc_emcee_window_attach(kmc_sampler_t s, const void *handles, int32_t nranks, int32_t rank);
 /* Device pointers of the ensemble state (x: [nw][d] FP64, logp: [nw] FP64, naccept: [nw] u32),
  * valid until kmc_emcee_destroy; for stream-ordered exchanges by the caller. */
 int32_t kmc_emcee_device_ptrs(kmc_sampler_t s, void **x, void **logp, void **naccept);
@@ -153,6 +179,32 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp,
 int32_t kmc_emcee_chain_moments(kmc_sampler_t s, double *mean, double *var, int64_t *count);
 /* Current ensemble: theta [nw][d], logp [nw], naccept [nw]; any may be NULL. */
 int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept);
+
+
+/* Library-owned multi-GPU (single process, SURVEY.md section 8b: opts {devices[], sharded / independent}) -------- */
+/* One emcee run over `ndev` devices of this process.  devices[] lists CUDA ordinals (an ordinal may repeat: its
+ * sub-samplers then share that GPU, which is how the sharded path is tested on one GPU).  densities[] holds one plugin
+ * handle per entry of devices[] (fused plugins keep no device memory, so the same handle may be repeated).
+ *   KMC_MULTI_SHARDED      theta0s is ONE ensemble [nwalkers][d]; entry r updates positions [r*S, (r+1)*S) of each half,
+ *                          S = nwalkers/2/ndev, with the push exchange over peer memory (cudaDeviceEnablePeerAccess);
+ *                          results are the reference 3 arrays for the WHOLE ensemble in global walker order,
+ *                          bit-identical to the single-GPU run.  Parallel region replaced: src/samplers.jl:246-273.
+ *   KMC_MULTI_INDEPENDENT  theta0s is [ndev][nwalkers][d]: ndev ensembles, ensemble r with walker ids r*nwalkers..,
+ *                          no communication; results are concatenated ensemble-major ([ndev*nwalkers] walkers).
+ * opts->device / shard_* / exchange / walker_id_base are filled in by the library. */
+int32_t kmc_emcee_create_multi(const kmc_density_t *densities, const double *theta0s, int64_t nwalkers, int32_t d,
+                               const kmc_emcee_opts *opts, const int32_t *devices, int32_t ndev, int32_t mode,
+                               kmc_multi_t *out);
+int32_t kmc_multi_destroy(kmc_multi_t m);
+/* Advance every device `niters` outer iterations (< 0: all that remain); asynchronous. */
+int32_t kmc_multi_run(kmc_multi_t m, int64_t niters);
+int32_t kmc_multi_sync(kmc_multi_t m);
+/* Device time of the last kmc_multi_run: the maximum over the devices' kernels.  Synchronises. */
+int32_t kmc_multi_last_run_ms(kmc_multi_t m, double *ms);
+/* Samples per walker and walkers in the result arrays (nwalkers, or ndev*nwalkers for independent ensembles). */
+int32_t kmc_multi_shape(kmc_multi_t m, int64_t *ns, int64_t *nwalkers_out);
+/* thetas [nw_out][ns][d], logp [nw_out][ns], accept_ratio [nw_out]; any may be NULL. */
+int32_t kmc_multi_copy_results(kmc_multi_t m, double *thetas, double *logp, double *accept_ratio);
 
 #ifdef __cplusplus
 }

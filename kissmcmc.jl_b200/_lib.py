@@ -13,6 +13,8 @@ PKG = Path(__file__).resolve().parent
 LIB_PATH = Path(os.environ["KMC_LIB"]) if os.environ.get("KMC_LIB") else PKG / "libkissmcmc_cuda.so"
 
 MODE_PHILOX, MODE_REPLAY = 0, 1
+EXCHANGE_REPLICA, EXCHANGE_PUSH = 0, 1
+MULTI_SHARDED, MULTI_INDEPENDENT = 0, 1
 
 # every symbol include/kissmcmc_cuda.h declares
 SYMBOLS = [
@@ -22,6 +24,9 @@ SYMBOLS = [
     "kmc_emcee_create", "kmc_emcee_destroy", "kmc_emcee_set_stream", "kmc_emcee_set_replay",
     "kmc_emcee_run", "kmc_emcee_run_half", "kmc_emcee_device_ptrs", "kmc_emcee_ipc_export", "kmc_emcee_set_peers", "kmc_emcee_nlocal", "kmc_emcee_sync", "kmc_emcee_last_run_ms", "kmc_emcee_progress",
     "kmc_emcee_nsamples", "kmc_emcee_copy_results", "kmc_emcee_copy_state", "kmc_emcee_chain_moments",
+    "kmc_emcee_window_export", "kmc_emcee_window_attach",
+    "kmc_emcee_create_multi", "kmc_multi_destroy", "kmc_multi_run", "kmc_multi_sync", "kmc_multi_last_run_ms",
+    "kmc_multi_shape", "kmc_multi_copy_results",
 ]
 
 
@@ -35,8 +40,9 @@ class EmceeOpts(C.Structure):
     _fields_ = [
         ("niter_walker", C.c_int64), ("nburnin_walker", C.c_int64), ("nthin", C.c_int64),
         ("a_scale", C.c_double), ("seed", C.c_uint64), ("mode", C.c_int32), ("device", C.c_int32),
-        ("walker_id_base", C.c_int64), ("launch_mode", C.c_int32), ("reserved", C.c_int32),
+        ("walker_id_base", C.c_int64), ("launch_mode", C.c_int32), ("exchange", C.c_int32),
         ("shard_begin", C.c_int64), ("shard_count", C.c_int64),
+        ("push_chunk", C.c_int32), ("push_cap", C.c_int32), ("push_lag", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -76,6 +82,16 @@ lib.kmc_emcee_nsamples.argtypes = [C.c_void_p, _i64p]
 lib.kmc_emcee_copy_results.argtypes = [C.c_void_p, _dp, _dp, _dp]
 lib.kmc_emcee_copy_state.argtypes = [C.c_void_p, _dp, _dp, _i64p]
 lib.kmc_emcee_chain_moments.argtypes = [C.c_void_p, _dp, _dp, _i64p]
+lib.kmc_emcee_window_export.argtypes = [C.c_void_p, C.c_void_p]
+lib.kmc_emcee_window_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
+lib.kmc_emcee_create_multi.argtypes = [C.POINTER(C.c_void_p), _dp, C.c_int64, C.c_int32, C.POINTER(EmceeOpts),
+                                       C.POINTER(C.c_int32), C.c_int32, C.c_int32, C.POINTER(C.c_void_p)]
+lib.kmc_multi_destroy.argtypes = [C.c_void_p]
+lib.kmc_multi_run.argtypes = [C.c_void_p, C.c_int64]
+lib.kmc_multi_sync.argtypes = [C.c_void_p]
+lib.kmc_multi_last_run_ms.argtypes = [C.c_void_p, _dp]
+lib.kmc_multi_shape.argtypes = [C.c_void_p, _i64p, _i64p]
+lib.kmc_multi_copy_results.argtypes = [C.c_void_p, _dp, _dp, _dp]
 for _name in SYMBOLS:
     if _name not in ("kmc_version", "kmc_last_error"):
         getattr(lib, _name).restype = C.c_int32

@@ -23,7 +23,8 @@ import warnings
 import numpy as np
 
 from . import _lib
-from ._lib import EmceeOpts, KmcError, MODE_PHILOX, MODE_REPLAY, check, lib
+from ._lib import (EXCHANGE_PUSH, EXCHANGE_REPLICA, EmceeOpts, KmcError, MODE_PHILOX, MODE_REPLAY, MULTI_INDEPENDENT,
+                   MULTI_SHARDED, check, lib)
 
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
@@ -127,7 +128,8 @@ class Sampler:
     """Owns a kmc_sampler_t.  Counts are PER WALKER (niter_walker = niter // nwalkers)."""
 
     def __init__(self, logdensity: LogDensity, theta0s, niter_walker, nburnin_walker, nthin=1, a_scale=2.0,
-                 seed=0, mode=MODE_PHILOX, device=None, walker_id_base=0, launch_mode=0, shard=None):
+                 seed=0, mode=MODE_PHILOX, device=None, walker_id_base=0, launch_mode=0, shard=None,
+                 exchange=EXCHANGE_REPLICA, push_chunk=0, push_cap=0, push_lag=0):
         x = np.ascontiguousarray(np.asarray(theta0s, dtype=np.float64))
         if x.ndim == 1:
             x = x.reshape(-1, 1)
@@ -135,8 +137,9 @@ class Sampler:
         self.logdensity = logdensity
         self.opts = EmceeOpts(int(niter_walker), int(nburnin_walker), int(nthin), float(a_scale), int(seed),
                               int(mode), int(logdensity.device if device is None else device),
-                              int(walker_id_base), int(launch_mode), 0,
-                              int(shard[0]) if shard else 0, int(shard[1]) if shard else 0)
+                              int(walker_id_base), int(launch_mode), int(exchange),
+                              int(shard[0]) if shard else 0, int(shard[1]) if shard else 0,
+                              int(push_chunk), int(push_cap), int(push_lag), 0)
         h = C.c_void_p()
         check(lib.kmc_emcee_create(logdensity._h, _ptr(x), self.nw, self.d, C.byref(self.opts), C.byref(h)))
         self._h = h
@@ -189,6 +192,16 @@ class Sampler:
         n = len(handles_x)
         check(lib.kmc_emcee_set_peers(self._h, b"".join(handles_x), b"".join(handles_flags), n, rank))
 
+    def window_export(self) -> bytes:
+        """The 64-byte CUDA IPC handle of a push-exchange sampler's window (positions + receive ring + flags)."""
+        hw = C.create_string_buffer(64)
+        check(lib.kmc_emcee_window_export(self._h, hw))
+        return hw.raw
+
+    def window_attach(self, handles, rank: int):
+        """All ranks' window handles (list of 64-byte strings, rank-major)."""
+        check(lib.kmc_emcee_window_attach(self._h, b"".join(handles), len(handles), rank))
+
     def device_ptrs(self):
         """(x, logp, naccept) device addresses: x [nw][d] f64, logp [nw] f64, naccept [nw] u32."""
         x, lp, na = C.c_void_p(), C.c_void_p(), C.c_void_p()
@@ -219,9 +232,68 @@ class Sampler:
         return mean, var, n.value
 
     def state(self):
-        x, lp, na = np.empty((self.nw, self.d)), np.empty(self.nw), np.empty(self.nw, dtype=np.int64)
+        """Current ensemble (x, logp, naccept); a push-exchange sampler returns the rows it holds
+        (its slice of half 0, then of half 1)."""
+        n = self.nl if self.opts.exchange == EXCHANGE_PUSH else self.nw
+        x, lp, na = np.empty((n, self.d)), np.empty(n), np.empty(n, dtype=np.int64)
         check(lib.kmc_emcee_copy_state(self._h, _ptr(x), _ptr(lp), _ptr(na, _i64p)))
         return x, lp, na
+
+
+class MultiSampler:
+    """Owns a kmc_multi_t: one emcee run over several GPUs of THIS process (library-owned multi-GPU).
+
+    sharded=True   ONE ensemble sharded by walker index over `devices` (push exchange over peer memory); results are
+                   those of the single-GPU run of the same ensemble, bit for bit.  theta0s [nw, d].
+    sharded=False  len(devices) independent ensembles, theta0s [ndev, nw, d]; results concatenated ensemble-major.
+    A device ordinal may repeat (its sub-samplers share the GPU) -- that is how the sharded path runs on one GPU."""
+
+    def __init__(self, logdensity, theta0s, niter_walker, nburnin_walker, nthin=1, a_scale=2.0, seed=0, devices=(0,),
+                 sharded=True, push_chunk=0, push_cap=0, push_lag=0):
+        devices = [int(v) for v in devices]
+        lds = list(logdensity) if isinstance(logdensity, (list, tuple)) else [logdensity] * len(devices)
+        assert len(lds) == len(devices)
+        x = np.ascontiguousarray(np.asarray(theta0s, dtype=np.float64))
+        if sharded:
+            x = x.reshape(len(x), -1)
+            self.nw, self.d = x.shape
+        else:
+            x = x.reshape(len(devices), x.shape[1], -1)
+            _, self.nw, self.d = x.shape
+        self._keep = lds
+        self.opts = EmceeOpts(int(niter_walker), int(nburnin_walker), int(nthin), float(a_scale), int(seed), MODE_PHILOX,
+                              0, 0, 0, 0, 0, 0, int(push_chunk), int(push_cap), int(push_lag), 0)
+        hs = (C.c_void_p * len(devices))(*[ld._h for ld in lds])
+        dv = (C.c_int32 * len(devices))(*devices)
+        h = C.c_void_p()
+        check(lib.kmc_emcee_create_multi(hs, _ptr(x), self.nw, self.d, C.byref(self.opts), dv, len(devices),
+                                         MULTI_SHARDED if sharded else MULTI_INDEPENDENT, C.byref(h)))
+        self._h = h
+        ns, nwo = C.c_int64(), C.c_int64()
+        check(lib.kmc_multi_shape(h, C.byref(ns), C.byref(nwo)))
+        self.ns, self.nw_out = ns.value, nwo.value
+
+    def close(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.kmc_multi_destroy(h)
+
+    __del__ = close
+
+    def run(self, niters: int = -1, sync: bool = True):
+        check(lib.kmc_multi_run(self._h, int(niters)))
+        if sync:
+            check(lib.kmc_multi_sync(self._h))
+
+    def last_run_ms(self) -> float:
+        ms = C.c_double()
+        check(lib.kmc_multi_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def results(self):
+        th, lp, ar = np.empty((self.nw_out, self.ns, self.d)), np.empty((self.nw_out, self.ns)), np.empty(self.nw_out)
+        check(lib.kmc_multi_copy_results(self._h, _ptr(th), _ptr(lp), _ptr(ar)))
+        return th, lp, ar
 
 
 # ------------------------------------------------------------------------------------------
@@ -236,8 +308,13 @@ def _require_plugin(logdensity):
 
 
 def emcee(logdensity, theta0s, *, niter=10**5, nburnin=None, nthin=1, a_scale=2.0, use_progress_meter=True,
-          hasblob=False, init_blobs=None, reduce_blob=None, seed=0, replay=None, launch_mode=0):
+          hasblob=False, init_blobs=None, reduce_blob=None, seed=0, replay=None, launch_mode=0, devices=None,
+          sharded=True):
     """The affine-invariant ensemble sampler; same call shape and 4-tuple as the reference.
+
+    devices=[0, 1, ...] runs on several GPUs of this process (library-owned, no torch): sharded=True shards the ONE
+    ensemble by walker index (same chains as a single GPU, bit for bit); sharded=False runs len(devices) independent
+    ensembles from theta0s [ndev, nw(, d)] and returns them concatenated.
 
     Returns (thetas, accept_ratio, logdensities, None): thetas[w] is walker w's chain
     ([nw, ns] for scalar theta, [nw, ns, d] otherwise), accept_ratio [nw], logdensities [nw, ns],
@@ -249,6 +326,20 @@ def emcee(logdensity, theta0s, *, niter=10**5, nburnin=None, nthin=1, a_scale=2.
         raise NotImplementedError("hasblob=True is not supported by the CUDA backend: blobs are arbitrary host "
                                   "objects (src/samplers.jl:194-196)")
     th = np.asarray(theta0s, dtype=np.float64)  # np.asarray + ascontiguousarray below = the deepcopy at :198
+    if devices is not None and not sharded:     # len(devices) independent ensembles, theta0s [ndev, nw(, d)]
+        if nburnin is None:
+            nburnin = niter // 2
+        scalar_theta = th.ndim == 2
+        nwalkers = th.shape[1]
+        assert a_scale > 1 and nwalkers % 2 == 0, "Use an even number of walkers."
+        m = MultiSampler(logdensity, th, niter // nwalkers, nburnin // nwalkers, nthin, a_scale, seed, devices=devices,
+                         sharded=False)
+        try:
+            m.run(-1)
+            thetas, logp, ratio = m.results()
+        finally:
+            m.close()
+        return (thetas[:, :, 0] if scalar_theta else thetas), ratio, logp, None
     scalar_theta = th.ndim == 1
     if nburnin is None:
         nburnin = niter // 2                    # :190
@@ -260,6 +351,19 @@ def emcee(logdensity, theta0s, *, niter=10**5, nburnin=None, nthin=1, a_scale=2.
     npar = 1 if scalar_theta else th.shape[1]
     assert nwalkers >= npar + 2, "Use more walkers: at least DOF+2, but better many more."  # :205
 
+    if devices is not None:
+        if replay is not None:
+            raise NotImplementedError("replay mode runs on one device")
+        m = MultiSampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, devices=devices,
+                         sharded=True)
+        try:
+            m.run(-1)
+            thetas, logp, ratio = m.results()
+        finally:
+            m.close()
+        if scalar_theta:
+            thetas = thetas[:, :, 0]
+        return thetas, ratio, logp, None
     mode = MODE_REPLAY if replay is not None else MODE_PHILOX
     s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, mode,
                 launch_mode=launch_mode)

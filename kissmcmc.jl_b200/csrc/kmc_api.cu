@@ -20,6 +20,7 @@
 #include "kmc_fused_gauss.cuh"
 #include "kmc_fused_gauss2.cuh"
 #include "kmc_kernels.cuh"
+#include "kmc_push.cuh"
 
 namespace {
 
@@ -112,6 +113,8 @@ struct Ops {
     const void *run_peer = nullptr;  // general kernel with cross-GPU partner gathers (Philox mode)
     const void *run_bulk[2] = {nullptr, nullptr};  // [peer] bulk (TMA) general kernel, Philox mode, even D >= 6
     size_t bulk_smem = 0;
+    const void *run_push = nullptr;  // sharded ensemble with owner-computes pushes (kmc_push.cuh), Philox mode, even D
+    size_t push_smem = 0;
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
     int block = 0;               // max threads per CTA of the run kernels
     int min_blocks = 1;          // CTAs per SM the kernels are compiled for
@@ -132,6 +135,12 @@ Ops make_ops() {
         o.run_bulk[1] = (const void *)kmc::emcee_bulk_kernel<Dn, D, true>;
         o.bulk_smem = (size_t)3 * kmc::kBulkThreads * D * 8 + 16;
     }
+    if constexpr (D % 2 == 0) {
+        o.run_push = (const void *)kmc::emcee_push_kernel<Dn, D>;
+        o.push_smem = (size_t)3 * kmc::kPushThreads * D * 8 + 2 * sizeof(unsigned long long) +
+                      sizeof(unsigned) * (2 * kmc::kPushSlots * kmc::kPushMaxRanks + kmc::kPushMaxRanks) +
+                      sizeof(unsigned short) * kmc::kPushMaxRounds * kmc::kPushThreads;
+    }
     if (D <= 4) {  // shared-memory-resident variant for small rows
         o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;
         o.run[1][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), true>;
@@ -148,16 +157,18 @@ Ops make_ops() {
 template <template <int> class Dn>
 bool ops_for_dim(int d, Ops &o) {
     switch (d) {
-        case 1: o = make_ops<Dn, 1>(); return true;
         case 2: o = make_ops<Dn, 2>(); return true;
+        case 10: o = make_ops<Dn, 10>(); return true;
+#ifndef KMC_FAST_BUILD  // experiment builds (build/variants/) compile d = 2 and d = 10 only
+        case 1: o = make_ops<Dn, 1>(); return true;
         case 3: o = make_ops<Dn, 3>(); return true;
         case 4: o = make_ops<Dn, 4>(); return true;
         case 5: o = make_ops<Dn, 5>(); return true;
         case 6: o = make_ops<Dn, 6>(); return true;
         case 8: o = make_ops<Dn, 8>(); return true;
-        case 10: o = make_ops<Dn, 10>(); return true;
         case 12: o = make_ops<Dn, 12>(); return true;
         case 16: o = make_ops<Dn, 16>(); return true;
+#endif
         default: return false;
     }
 }
@@ -452,11 +463,31 @@ struct kmc_sampler_s {
     unsigned long long epoch = 0;
     std::vector<void *> ipc_opened;
     BatchScratch bsc;
+    // local layout of x / lp / nacc: rows held, offset of half 1, offset of this sampler's slice inside a half
+    long long nstate = 0, hoff = 0, loff = 0;
+    // push mode (KMC_EXCHANGE_PUSH, kmc_push.cuh): positions + receive ring + chunk flags in one window allocation
+    bool push = false, attached = false;
+    unsigned char *window = nullptr;
+    size_t win_flags = 0, win_recv = 0, win_x = 0, win_bytes = 0;  // byte offsets inside the window (same on every rank)
+    unsigned long long *task_ctr = nullptr;
+    int G = 1;
+    unsigned chunk = 0, rounds = 0, nchunks = 0, cap = 0, lag = 0;
+    double *peer_recv[8] = {};
+    int share = 1;  // sub-samplers sharing this device (kmc_emcee_create_multi with a repeated ordinal)
 };
+
+namespace {
+// Wire rank r's window (base address as seen from this sampler's device) into the push kernel's peer tables.
+void push_set_peer(kmc_sampler_s *s, int r, unsigned char *base) {
+    s->peer_recv[r] = reinterpret_cast<double *>(base + s->win_recv);
+    s->peer_flags[r] = reinterpret_cast<unsigned long long *>(base + s->win_flags);
+    s->peer_x[r] = reinterpret_cast<const double *>(base + s->win_x);
+}
+}  // namespace
 
 extern "C" {
 
-int32_t kmc_version(void) { return 100; }
+int32_t kmc_version(void) { return 200; }
 
 const char *kmc_last_error(void) { return g_err.c_str(); }
 
@@ -667,7 +698,9 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     if (!s) return KMC_OK;
     cudaSetDevice(s->opts.device);
     if (s->stream) cudaStreamSynchronize(s->stream);  // cached blocks must be idle before reuse
-    dev_free(s->x);
+    if (s->push) cudaFree(s->window);  // own allocation (exported through CUDA IPC); x lives inside it
+    else dev_free(s->x);
+    dev_free(s->task_ctr);
     dev_free(s->lp);
     dev_free(s->chain_x);
     dev_free(s->chain_lp);
@@ -715,13 +748,6 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
                     density->device, opts->device);
 
     CU_TRY(cudaSetDevice(opts->device));
-    if (const char *g = getenv("KMC_L2_FETCH")) {  // experiment: L2 fetch granularity (bytes) for random row gathers
-        size_t before = 0, after = 0;
-        cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-        cudaError_t e = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
-        cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-        fprintf(stderr, "KMC_L2_FETCH: %zu -> %zu (%s)\n", before, after, cudaGetErrorString(e));
-    }
     auto *s = new kmc_sampler_s;
     s->dn = density;
     s->opts = *opts;
@@ -738,6 +764,36 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     }
     const long long nspan = opts->niter_walker - opts->nburnin_walker;
     s->ns = nspan > 0 ? nspan / opts->nthin : 0;  // :234
+    s->push = opts->exchange == KMC_EXCHANGE_PUSH;
+    if (opts->exchange != KMC_EXCHANGE_REPLICA && opts->exchange != KMC_EXCHANGE_PUSH) {
+        delete s;
+        return fail(KMC_ERR_INVALID, "unknown exchange %d", opts->exchange);
+    }
+    if (s->push) {  // owner-computes push exchange: equal shards, fused plugin with 16-byte-multiple rows, Philox draws
+        const char *why = nullptr;
+        if (opts->shard_count <= 0 || s->nhalf % s->scnt || s->sbeg % s->scnt) why = "equal shards: rank r owns [r*S, (r+1)*S) of each half";
+        else if (s->nhalf / s->scnt > kmc::kPushMaxRanks) why = "at most 8 ranks";
+        else if (density->ops.batch || !density->ops.run_push) why = "a fused (non-batched) plugin with even d";
+        else if (opts->mode != KMC_MODE_PHILOX || opts->launch_mode != 0) why = "Philox draws and launch_mode 0";
+        else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxRounds * kmc::kPushThreads) why = "push_chunk in [0, 1024]";
+        else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushThreads) why = "push_cap in [0, 256]";
+        else if (opts->push_lag < 0) why = "push_lag >= 0";
+        if (why) {
+            delete s;
+            return fail(KMC_ERR_UNSUPPORTED, "the push exchange needs %s", why);
+        }
+        s->G = (int)(s->nhalf / s->scnt);
+        s->rank = (int)(s->sbeg / s->scnt);
+        s->chunk = opts->push_chunk > 0 ? (unsigned)opts->push_chunk
+                                        : (unsigned)std::min<long long>(1024, std::max<long long>(256, 128LL * s->G));
+        s->chunk = (unsigned)std::min<long long>(s->chunk, std::max<long long>(s->scnt, 1));
+        s->rounds = (s->chunk + kmc::kPushThreads - 1) / kmc::kPushThreads;
+        s->nchunks = (unsigned)((s->scnt + s->chunk - 1) / s->chunk);
+        s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : 192u;
+    }
+    s->nstate = s->push ? 2 * s->scnt : s->nw;
+    s->hoff = s->push ? s->scnt : s->nhalf;
+    s->loff = s->push ? 0 : s->sbeg;
 
     auto bail = [&](int32_t rc) {
         kmc_emcee_destroy(s);
@@ -755,9 +811,22 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     s->stream = s->own_stream;
     CU_TRY_S(cudaEventCreate(&s->ev0));
     CU_TRY_S(cudaEventCreate(&s->ev1));
-    CU_TRY_S(dev_alloc(&s->x, sizeof(double) * s->nw * d, opts->device));
-    CU_TRY_S(dev_alloc(&s->lp, sizeof(double) * s->nw, opts->device));
-    CU_TRY_S(dev_alloc(&s->nacc, sizeof(unsigned) * s->nw, opts->device));
+    if (s->push) {  // one window: [chunk flags | receive ring | positions], exported as ONE CUDA IPC handle
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        s->win_flags = 0;
+        s->win_recv = up(sizeof(unsigned long long) * (size_t)s->G * s->nchunks);
+        s->win_x = s->win_recv + up(sizeof(double) * 2 * (size_t)s->G * s->nchunks * s->cap * d);
+        s->win_bytes = s->win_x + up(sizeof(double) * (size_t)s->nstate * d);
+        CU_TRY_S(cudaMalloc(&s->window, s->win_bytes));
+        CU_TRY_S(cudaMemsetAsync(s->window, 0, s->win_recv, s->stream));  // flags = 0: nothing has landed
+        s->x = reinterpret_cast<double *>(s->window + s->win_x);
+        push_set_peer(s, s->rank, s->window);
+        CU_TRY_S(dev_alloc(&s->task_ctr, sizeof(unsigned long long), opts->device));
+    } else {
+        CU_TRY_S(dev_alloc(&s->x, sizeof(double) * s->nw * d, opts->device));
+    }
+    CU_TRY_S(dev_alloc(&s->lp, sizeof(double) * s->nstate, opts->device));
+    CU_TRY_S(dev_alloc(&s->nacc, sizeof(unsigned) * s->nstate, opts->device));
     CU_TRY_S(dev_alloc(&s->barrier, sizeof(unsigned long long), opts->device));
     CU_TRY_S(dev_alloc(&s->scratch, 4 * sizeof(unsigned long long), opts->device));
     CU_TRY_S(cudaMalloc(&s->flags, 8 * sizeof(unsigned long long)));  // own allocation: exported through CUDA IPC
@@ -766,9 +835,16 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         CU_TRY_S(dev_alloc(&s->chain_x, sizeof(double) * s->ns * s->nl * d, opts->device));
         CU_TRY_S(dev_alloc(&s->chain_lp, sizeof(double) * s->ns * s->nl, opts->device));
     }
-    CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nw, s->stream));
+    CU_TRY_S(cudaMemsetAsync(s->nacc, 0, sizeof(unsigned) * s->nstate, s->stream));
     CU_TRY_S(cudaMemsetAsync(s->barrier, 0, sizeof(unsigned long long), s->stream));
-    CU_TRY_S(cudaMemcpyAsync(s->x, theta0s, sizeof(double) * s->nw * d, cudaMemcpyHostToDevice, s->stream));
+    if (s->push) {  // only this shard's rows: its slice of half 0, then of half 1
+        CU_TRY_S(cudaMemcpyAsync(s->x, theta0s + (size_t)s->sbeg * d, sizeof(double) * s->scnt * d,
+                                 cudaMemcpyHostToDevice, s->stream));
+        CU_TRY_S(cudaMemcpyAsync(s->x + (size_t)s->scnt * d, theta0s + (size_t)(s->nhalf + s->sbeg) * d,
+                                 sizeof(double) * s->scnt * d, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        CU_TRY_S(cudaMemcpyAsync(s->x, theta0s, sizeof(double) * s->nw * d, cudaMemcpyHostToDevice, s->stream));
+    }
     if (density->ops.batch) {  // initial log-densities, :209-210, and the proposal buffers of the active shard
         CU_TRY_S(launch_batch_logp(*density, s->x, s->nw, s->lp, s->bsc, s->stream));
         CU_TRY_S(dev_alloc(&s->bb.Y, sizeof(double) * s->scnt * d, opts->device));
@@ -777,13 +853,25 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         CU_TRY_S(dev_alloc(&s->bb.p1, sizeof(double) * s->scnt, opts->device));
         CU_TRY_S(dev_alloc(&s->bb.j, sizeof(unsigned) * s->scnt, opts->device));
     } else {
-        long long nwl = s->nw;
+        long long nwl = s->nstate;
         void *args[] = {&s->x, &s->lp, &nwl, density->params.data()};
-        CU_TRY_S(cudaLaunchKernel(density->ops.eval, dim3((unsigned)((s->nw + 255) / 256)), dim3(256), args, 0,
+        CU_TRY_S(cudaLaunchKernel(density->ops.eval, dim3((unsigned)((s->nstate + 255) / 256)), dim3(256), args, 0,
                                   s->stream));
     }
     CU_TRY_S(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, opts->device));
-    if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
+    if (s->push) {  // one persistent kernel, tasks handed out dynamically: as many CTAs as fit
+        const void *kp = density->ops.run_push;
+        CU_TRY_S(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density->ops.push_smem));
+        int occ = 0;
+        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, kmc::kPushThreads, density->ops.push_smem));
+        if (occ < 1) return bail(fail(KMC_ERR_CUDA, "the push kernel does not fit on the device"));
+        s->grid = (unsigned)(occ * s->nsm);
+        s->block = kmc::kPushThreads;
+        s->smem_bytes = density->ops.push_smem;
+        s->lag = opts->push_lag > 0 ? (unsigned)opts->push_lag
+                                    : (unsigned)((3 * s->grid / 2 + std::max(1, s->G - 1) - 1) / std::max(1, s->G - 1));
+        s->lag = std::min(s->lag, s->nchunks);
+    } else if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
         auto geometry = [&](const void *kern, int maxblk, int ctas_per_sm, size_t smem_per_walker, bool &fits) {
@@ -968,6 +1056,39 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
         p.rank = s->rank;
         p.epoch_base = s->epoch;
     }
+    if (s->push) {  // sharded ensemble, owner-computes pushes (kmc_push.cuh): one persistent kernel for the whole range
+        if (s->G > 1 && !s->attached)
+            return fail(KMC_ERR_STATE, "push exchange: attach the peers' windows first (kmc_emcee_window_attach)");
+        kmc::PushParams q{};
+        q.recv = reinterpret_cast<double *>(s->window + s->win_recv);
+        q.flags = reinterpret_cast<unsigned long long *>(s->window + s->win_flags);
+        for (int r = 0; r < s->G; ++r) {
+            q.peer_recv[r] = s->peer_recv[r];
+            q.peer_flags[r] = s->peer_flags[r];
+            q.peer_x[r] = s->peer_x[r];
+        }
+        q.task_ctr = s->task_ctr;
+        q.S = (unsigned)s->scnt;
+        q.G = (unsigned)s->G;
+        q.rank = (unsigned)s->rank;
+        q.chunk = s->chunk;
+        q.rounds = s->rounds;
+        q.nchunks = s->nchunks;
+        q.cap = s->cap;
+        q.lag = s->lag;
+        set_range(hbeg, hend);
+        CU_TRY(cudaMemsetAsync(s->task_ctr, 0, sizeof(unsigned long long), s->stream));
+        CU_TRY(cudaEventRecord(s->ev0, s->stream));
+        void *pargs[] = {&p, &q, s->dn->params.data()};
+        CU_TRY(cudaLaunchCooperativeKernel(s->dn->ops.run_push, dim3(s->grid), dim3(s->block), pargs, s->smem_bytes,
+                                           s->stream));
+        s->bar_base += (unsigned long long)(hend - hbeg - 1) * s->grid;
+        s->last_launches = 1;
+        CU_TRY(cudaEventRecord(s->ev1, s->stream));
+        s->timed = true;
+        s->hdone = hend;
+        return KMC_OK;
+    }
     CU_TRY(cudaEventRecord(s->ev0, s->stream));
     if (s->dn->ops.batch) {  // propose -> batched log-density -> accept, per half-step
         const unsigned grid = (unsigned)((s->scnt * 32 + 255) / 256);
@@ -1081,6 +1202,7 @@ int32_t kmc_emcee_ipc_export(kmc_sampler_t s, void *handle_x, void *handle_flags
     if (!s || !handle_x || !handle_flags) return fail(KMC_ERR_INVALID, "NULL argument");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
     CU_TRY(cudaSetDevice(s->opts.device));
+    if (s->push) return fail(KMC_ERR_STATE, "a push-exchange sampler exports its window (kmc_emcee_window_export)");
     CU_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_x), s->x));
     CU_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle_flags), s->flags));
     return KMC_OK;
@@ -1090,6 +1212,7 @@ int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *
                             int32_t rank) {
     if (!s || !handles_x || !handles_flags) return fail(KMC_ERR_INVALID, "NULL argument");
     if (nranks < 1 || nranks > 8 || rank < 0 || rank >= nranks) return fail(KMC_ERR_INVALID, "bad rank / nranks (max 8)");
+    if (s->push) return fail(KMC_ERR_STATE, "a push-exchange sampler attaches windows (kmc_emcee_window_attach)");
     if (s->scnt * nranks != s->nhalf || s->sbeg != (long long)rank * s->scnt)
         return fail(KMC_ERR_INVALID, "peer mode needs equal shards: rank r owns [r*S, (r+1)*S) of each half");
     CU_TRY(cudaSetDevice(s->opts.device));
@@ -1111,6 +1234,35 @@ int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *
     }
     s->npeers = nranks;
     s->rank = rank;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_window_export(kmc_sampler_t s, void *handle) {
+    if (!s || !handle) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (!s->push) return fail(KMC_ERR_STATE, "not a push-exchange sampler (opts.exchange = KMC_EXCHANGE_PUSH)");
+    CU_TRY(cudaSetDevice(s->opts.device));
+    CU_TRY(cudaIpcGetMemHandle(reinterpret_cast<cudaIpcMemHandle_t *>(handle), s->window));
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_window_attach(kmc_sampler_t s, const void *handles, int32_t nranks, int32_t rank) {
+    if (!s || !handles) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (!s->push) return fail(KMC_ERR_STATE, "not a push-exchange sampler (opts.exchange = KMC_EXCHANGE_PUSH)");
+    if (nranks != s->G || rank != s->rank)
+        return fail(KMC_ERR_INVALID, "the sampler's shard is rank %d of %d, got rank %d of %d", s->rank, s->G, rank, nranks);
+    CU_TRY(cudaSetDevice(s->opts.device));
+    const cudaIpcMemHandle_t *hw = reinterpret_cast<const cudaIpcMemHandle_t *>(handles);
+    for (int r = 0; r < nranks; ++r) {
+        if (r == rank) {
+            push_set_peer(s, r, s->window);
+            continue;
+        }
+        void *pw = nullptr;
+        CU_TRY(cudaIpcOpenMemHandle(&pw, hw[r], cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(pw);
+        push_set_peer(s, r, static_cast<unsigned char *>(pw));
+    }
+    s->attached = true;
     return KMC_OK;
 }
 
@@ -1149,18 +1301,19 @@ int32_t kmc_emcee_progress(kmc_sampler_t s, int64_t *iters_done, double *naccept
     unsigned long long *sum = s->scratch, *outl = s->scratch + 1;
     double *ssq = reinterpret_cast<double *>(s->scratch + 2);
     CU_TRY(cudaMemsetAsync(s->scratch, 0, 4 * sizeof(unsigned long long), s->stream));
-    const unsigned grid = (unsigned)std::min<long long>((s->nw + 255) / 256, 1184);
-    kmc::nacc_sum_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, sum);
+    const long long nst = s->nstate;  // the whole ensemble, or this shard's walkers for a push-exchange sampler
+    const unsigned grid = (unsigned)std::min<long long>((nst + 255) / 256, 1184);
+    kmc::nacc_sum_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, nst, sum);
     unsigned long long hsum = 0, houtl = 0;
     double hssq = 0.0;
     CU_TRY(cudaMemcpyAsync(&hsum, sum, sizeof hsum, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    const double mean = (double)hsum / (double)s->nw;  // :276
-    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, mean, -1.0, ssq, nullptr);
+    const double mean = (double)hsum / (double)nst;  // :276
+    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, nst, mean, -1.0, ssq, nullptr);
     CU_TRY(cudaMemcpyAsync(&hssq, ssq, sizeof hssq, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    const double sd = std::sqrt(hssq / (double)(s->nw - 1));  // :277 sqrt(var(naccept))
-    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, s->nw, mean, 2.0 * sd, nullptr, outl);  // :278
+    const double sd = std::sqrt(hssq / (double)(nst - 1));  // :277 sqrt(var(naccept))
+    kmc::nacc_moment_kernel<<<grid, 256, 0, s->stream>>>(s->nacc, nst, mean, 2.0 * sd, nullptr, outl);  // :278
     CU_TRY(cudaMemcpyAsync(&houtl, outl, sizeof houtl, cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     CU_TRY(cudaGetLastError());
@@ -1220,8 +1373,8 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
     }
     if (accept_ratio) {  // this sampler's walkers: its slice of half 0, then of half 1
         std::vector<unsigned> h(nl);
-        CU_TRY(cudaMemcpy(h.data(), s->nacc + s->sbeg, sizeof(unsigned) * s->scnt, cudaMemcpyDeviceToHost));
-        CU_TRY(cudaMemcpy(h.data() + s->scnt, s->nacc + s->nhalf + s->sbeg, sizeof(unsigned) * s->scnt,
+        CU_TRY(cudaMemcpy(h.data(), s->nacc + s->loff, sizeof(unsigned) * s->scnt, cudaMemcpyDeviceToHost));
+        CU_TRY(cudaMemcpy(h.data() + s->scnt, s->nacc + s->hoff + s->loff, sizeof(unsigned) * s->scnt,
                           cudaMemcpyDeviceToHost));
         const double den = (double)(s->opts.niter_walker - s->opts.nburnin_walker);  // :291
         for (long long w = 0; w < nl; ++w) accept_ratio[w] = (double)h[w] / den;
@@ -1261,12 +1414,178 @@ int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64
     if (!s) return fail(KMC_ERR_INVALID, "NULL sampler");
     CU_TRY(cudaSetDevice(s->opts.device));
     CU_TRY(cudaStreamSynchronize(s->stream));
-    if (theta) CU_TRY(cudaMemcpy(theta, s->x, sizeof(double) * s->nw * s->d, cudaMemcpyDeviceToHost));
-    if (logp) CU_TRY(cudaMemcpy(logp, s->lp, sizeof(double) * s->nw, cudaMemcpyDeviceToHost));
+    const long long nst = s->nstate;  // push exchange: the rows this shard holds (its slice of half 0, then of half 1)
+    if (theta) CU_TRY(cudaMemcpy(theta, s->x, sizeof(double) * nst * s->d, cudaMemcpyDeviceToHost));
+    if (logp) CU_TRY(cudaMemcpy(logp, s->lp, sizeof(double) * nst, cudaMemcpyDeviceToHost));
     if (naccept) {
-        std::vector<unsigned> h(s->nw);
-        CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * s->nw, cudaMemcpyDeviceToHost));
-        for (long long w = 0; w < s->nw; ++w) naccept[w] = h[w];
+        std::vector<unsigned> h(nst);
+        CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * nst, cudaMemcpyDeviceToHost));
+        for (long long w = 0; w < nst; ++w) naccept[w] = h[w];
+    }
+    return KMC_OK;
+}
+
+// ------------------------------------------------------------------ library-owned multi-GPU (single process)
+}  // extern "C"
+
+struct kmc_multi_s {
+    int mode = KMC_MULTI_SHARDED;
+    long long nw = 0;  // walkers per ensemble
+    int d = 0;
+    std::vector<kmc_sampler_s *> subs;
+};
+
+extern "C" {
+
+int32_t kmc_multi_destroy(kmc_multi_t m) {
+    if (!m) return KMC_OK;
+    for (auto *s : m->subs)  // nobody tears its window down while a peer's kernel may still write into it
+        if (s) {
+            cudaSetDevice(s->opts.device);
+            cudaStreamSynchronize(s->stream);
+        }
+    for (auto *s : m->subs) kmc_emcee_destroy(s);
+    delete m;
+    return KMC_OK;
+}
+
+int32_t kmc_emcee_create_multi(const kmc_density_t *densities, const double *theta0s, int64_t nwalkers, int32_t d,
+                               const kmc_emcee_opts *opts, const int32_t *devices, int32_t ndev, int32_t mode,
+                               kmc_multi_t *out) {
+    if (!out) return fail(KMC_ERR_INVALID, "out is NULL");
+    *out = nullptr;
+    if (!densities || !theta0s || !opts || !devices) return fail(KMC_ERR_INVALID, "NULL argument");
+    if (ndev < 1 || ndev > kmc::kPushMaxRanks) return fail(KMC_ERR_INVALID, "ndev must be in [1, 8]");
+    if (mode != KMC_MULTI_SHARDED && mode != KMC_MULTI_INDEPENDENT) return fail(KMC_ERR_INVALID, "unknown mode %d", mode);
+    for (int r = 0; r < ndev; ++r)
+        if (!densities[r]) return fail(KMC_ERR_INVALID, "densities[%d] is NULL", r);
+    if (mode == KMC_MULTI_SHARDED && (nwalkers < 2 || (nwalkers & 1) || (nwalkers / 2) % ndev))
+        return fail(KMC_ERR_INVALID, "nwalkers/2 must be a multiple of the number of devices");
+    auto *m = new kmc_multi_s;
+    m->mode = mode;
+    m->nw = nwalkers;
+    m->d = d;
+    m->subs.assign(ndev, nullptr);
+    auto bail = [&](int32_t rc) {
+        const std::string keep = g_err;
+        kmc_multi_destroy(m);
+        g_err = keep;
+        return rc;
+    };
+    const long long S = nwalkers / 2 / ndev;
+    for (int r = 0; r < ndev; ++r) {
+        kmc_emcee_opts o = *opts;
+        o.device = devices[r];
+        if (mode == KMC_MULTI_SHARDED) {
+            o.exchange = KMC_EXCHANGE_PUSH;
+            o.shard_begin = r * S;
+            o.shard_count = S;
+            o.launch_mode = 0;
+        } else {  // independent ensembles: disjoint walker ids => disjoint Philox streams
+            o.exchange = KMC_EXCHANGE_REPLICA;
+            o.shard_begin = o.shard_count = 0;
+            o.walker_id_base = opts->walker_id_base + (int64_t)r * nwalkers;
+        }
+        const double *th = mode == KMC_MULTI_SHARDED ? theta0s : theta0s + (size_t)r * nwalkers * d;
+        const int32_t rc = kmc_emcee_create(densities[r], th, nwalkers, d, &o, &m->subs[r]);
+        if (rc != KMC_OK) return bail(rc);
+    }
+    if (mode == KMC_MULTI_SHARDED) {
+        for (int a = 0; a < ndev; ++a) {
+            kmc_sampler_s *sa = m->subs[a];
+            int share = 0;
+            for (int b = 0; b < ndev; ++b) share += devices[b] == devices[a] ? 1 : 0;
+            sa->share = share;  // sub-samplers of one GPU must all be co-resident: split the CTA slots
+            sa->grid = std::max(1u, sa->grid / (unsigned)share);
+            sa->lag = std::min(sa->nchunks, (unsigned)((3 * sa->grid / 2 + std::max(1, ndev - 1) - 1) / std::max(1, ndev - 1)));
+            if (opts->push_lag > 0) sa->lag = std::min(sa->nchunks, (unsigned)opts->push_lag);
+            if (cudaSetDevice(devices[a]) != cudaSuccess) return bail(fail(KMC_ERR_CUDA, "cudaSetDevice(%d) failed", devices[a]));
+            for (int b = 0; b < ndev; ++b) {
+                if (devices[b] != devices[a]) {
+                    int can = 0;
+                    cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
+                    if (!can) return bail(fail(KMC_ERR_CUDA, "device %d cannot access device %d's memory", devices[a], devices[b]));
+                    const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
+                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                        return bail(fail(KMC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devices[a], devices[b],
+                                         cudaGetErrorString(e)));
+                    cudaGetLastError();
+                }
+                push_set_peer(sa, b, m->subs[b]->window);
+            }
+            sa->attached = true;
+        }
+    }
+    *out = m;
+    return KMC_OK;
+}
+
+int32_t kmc_multi_run(kmc_multi_t m, int64_t niters) {
+    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
+    for (auto *s : m->subs) {  // asynchronous launches: the devices' kernels synchronise among themselves
+        const int32_t rc = kmc_emcee_run(s, niters);
+        if (rc != KMC_OK) return rc;
+    }
+    return KMC_OK;
+}
+
+int32_t kmc_multi_sync(kmc_multi_t m) {
+    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
+    for (auto *s : m->subs) {
+        const int32_t rc = kmc_emcee_sync(s);
+        if (rc != KMC_OK) return rc;
+    }
+    return KMC_OK;
+}
+
+int32_t kmc_multi_last_run_ms(kmc_multi_t m, double *ms) {
+    if (!m || !ms) return fail(KMC_ERR_INVALID, "NULL argument");
+    *ms = 0.0;
+    for (auto *s : m->subs) {
+        double v = 0.0;
+        const int32_t rc = kmc_emcee_last_run_ms(s, &v, nullptr);
+        if (rc != KMC_OK) return rc;
+        *ms = std::max(*ms, v);
+    }
+    return KMC_OK;
+}
+
+int32_t kmc_multi_shape(kmc_multi_t m, int64_t *ns, int64_t *nwalkers_out) {
+    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
+    if (ns) *ns = m->subs[0]->ns;
+    if (nwalkers_out) *nwalkers_out = m->mode == KMC_MULTI_SHARDED ? m->nw : m->nw * (long long)m->subs.size();
+    return KMC_OK;
+}
+
+int32_t kmc_multi_copy_results(kmc_multi_t m, double *thetas, double *logp, double *accept_ratio) {
+    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
+    const long long ns = m->subs[0]->ns, nw = m->nw;
+    const int d = m->d, ndev = (int)m->subs.size();
+    if (m->mode == KMC_MULTI_INDEPENDENT) {
+        for (int r = 0; r < ndev; ++r) {
+            const int32_t rc = kmc_emcee_copy_results(m->subs[r], thetas ? thetas + (size_t)r * nw * ns * d : nullptr,
+                                                      logp ? logp + (size_t)r * nw * ns : nullptr,
+                                                      accept_ratio ? accept_ratio + (size_t)r * nw : nullptr);
+            if (rc != KMC_OK) return rc;
+        }
+        return KMC_OK;
+    }
+    // sharded: sub r returns its slice of half 0 then of half 1 ([2S] walkers); global order = all slices of half 0, then of half 1
+    const long long S = nw / 2 / ndev;
+    std::vector<double> th, lp, ar;
+    if (thetas) th.resize((size_t)2 * S * ns * d);
+    if (logp) lp.resize((size_t)2 * S * ns);
+    if (accept_ratio) ar.resize((size_t)2 * S);
+    for (int r = 0; r < ndev; ++r) {
+        const int32_t rc = kmc_emcee_copy_results(m->subs[r], thetas ? th.data() : nullptr, logp ? lp.data() : nullptr,
+                                                  accept_ratio ? ar.data() : nullptr);
+        if (rc != KMC_OK) return rc;
+        for (int b = 0; b < 2; ++b) {
+            const size_t dst = (size_t)b * (nw / 2) + (size_t)r * S, src = (size_t)b * S;
+            if (thetas) memcpy(thetas + dst * ns * d, th.data() + src * ns * d, sizeof(double) * S * ns * d);
+            if (logp) memcpy(logp + dst * ns, lp.data() + src * ns, sizeof(double) * S * ns);
+            if (accept_ratio) memcpy(accept_ratio + dst, ar.data() + src, sizeof(double) * S);
+        }
     }
     return KMC_OK;
 }

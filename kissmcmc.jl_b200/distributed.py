@@ -17,6 +17,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
+from ._lib import EXCHANGE_PUSH
 from .api import LogDensity, Sampler, _require_plugin
 
 
@@ -59,7 +60,7 @@ def _gather_numpy(local: np.ndarray, group=None):
 
 
 def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=2.0, seed=0, group=None,
-                  sampler_factory=None, x_view=None, exchange="allgather"):
+                  sampler_factory=None, x_view=None, exchange="allgather", push_opts=None):
     """emcee (src/samplers.jl:188-216) of one ensemble sharded over the ranks of `group`.
 
     Every rank passes the SAME theta0s ([nw] or [nw, d]).  Returns the reference 4-tuple for
@@ -68,7 +69,12 @@ def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=
     exchange="allgather": one launch per half-step + NCCL all-gather of the updated half.
     exchange="peer":      ONE persistent kernel per rank; partner rows are gathered straight from
                           the owner GPU's memory over NVLink (CUDA IPC) and the ranks meet at a
-                          flag barrier in peer memory per half-step -- no collective at all."""
+                          flag barrier in peer memory per half-step -- no collective at all.
+    exchange="push":      ONE persistent kernel per rank, every rank holds ONLY its shard: the owners
+                          of the passive half push the packed partner rows each peer's walkers will
+                          ask for into the peer's receive ring (bulk stores over NVLink) and every
+                          consumer starts as soon as ITS chunk's rows have landed -- no collective, no
+                          cross-GPU barrier (csrc/kmc_push.cuh)."""
     rank, world = dist.get_rank(group), dist.get_world_size(group)
     th = np.asarray(theta0s, dtype=np.float64)
     scalar_theta = th.ndim == 1
@@ -85,6 +91,26 @@ def emcee_sharded(logdensity, theta0s, *, niter, nburnin=None, nthin=1, a_scale=
 
     import contextlib
     ctx = contextlib.nullcontext()
+    if sampler_factory is None and exchange == "push":
+        _require_plugin(logdensity)
+        s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, launch_mode=0,
+                    shard=(begin, count), exchange=EXCHANGE_PUSH, **(push_opts or {}))
+        try:
+            allh = [None] * world
+            dist.all_gather_object(allh, s.window_export(), group=group)
+            s.window_attach(allh, rank)
+            dist.barrier(group)                 # every rank's window is mapped and its initial state in place
+            s.run(-1, sync=True)                # the kernels of all ranks synchronise among themselves
+            dist.barrier(group)                 # nobody tears its window down while a peer still writes into it
+            lth, llp, lar = s.results()
+        finally:
+            s.close()
+        thetas = assemble_shards(_gather_numpy(lth, group), nwalkers)
+        logp = assemble_shards(_gather_numpy(llp, group), nwalkers)
+        ratio = assemble_shards(_gather_numpy(lar, group), nwalkers)
+        if scalar_theta:
+            thetas = thetas[:, :, 0]
+        return thetas, ratio, logp, None
     if sampler_factory is None and exchange == "peer":
         _require_plugin(logdensity)
         s = Sampler(logdensity, th, niter_walker, nburnin_walker, nthin, a_scale, seed, launch_mode=0,

@@ -45,9 +45,13 @@ struct EmceeOpts
     device::Int32
     walker_id_base::Int64
     launch_mode::Int32
-    reserved::Int32
+    exchange::Int32
     shard_begin::Int64
     shard_count::Int64
+    push_chunk::Int32
+    push_cap::Int32
+    push_lag::Int32
+    reserved::Int32
 end
 
 # ------------------------------------------------------------------ log-density plugins
@@ -127,7 +131,7 @@ function emcee(ld::LogDensity, theta0s; niter=10^5, nburnin=niter ÷ 2, nthin=1,
     @assert nwalkers >= d + 2 "Use more walkers: at least DOF+2, but better many more."   # :205
 
     opts = Ref(EmceeOpts(niter_walker, nburnin_walker, nthin, a_scale, UInt64(seed),
-                         replay === nothing ? MODE_PHILOX : MODE_REPLAY, device, 0, 0, 0, 0, 0))
+                         replay === nothing ? MODE_PHILOX : MODE_REPLAY, device, 0, 0, 0, 0, 0, 0, 0, 0, 0))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve x0 check(ccall((:kmc_emcee_create, LIB[]), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Int64, Int32, Ref{EmceeOpts}, Ref{Ptr{Cvoid}}),

@@ -27,10 +27,10 @@ def header_functions():
 
 def test_opts_struct_is_the_same_in_c_ctypes_and_julia(km):
     fields = header_struct_fields()
-    assert len(fields) == 12
+    assert len(fields) == 16
     opts = km.EmceeOpts if hasattr(km, "EmceeOpts") else km._lib.EmceeOpts
     assert [(n, t) for n, t in opts._fields_] == [(name, C_TO_CTYPES[ct]) for ct, name in fields]
-    assert C.sizeof(opts) == 80                                       # naturally aligned, no padding
+    assert C.sizeof(opts) == 96                                       # naturally aligned, no padding
     jl = re.search(r"struct EmceeOpts\n(.*?)\nend", JULIA, re.S).group(1)
     jl_fields = re.findall(r"^\s*(\w+)::(\w+)\s*$", jl, re.M)
     assert jl_fields == [(name, C_TO_JULIA[ct]) for ct, name in fields]
