@@ -103,13 +103,17 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                            const void *data, int64_t data_bytes, int32_t device,
                            kmc_density_t *out);
 int32_t kmc_density_destroy(kmc_density_t h);
-/* Options: "tensor_cores" = 0/1 (logistic with d = 32 and bf16-representable data runs its
- * walkers x data logits GEMM on tcgen05 tensor cores by default; 0 forces the FP64 kernel; the
- * dense Gaussian with 16 < d <= 128 is exact FP64 by default and opts in with 1).
+/* Options: "tensor_cores" = 0/1.  Every plugin is exact FP64 by default.  1 opts in to the tcgen05 kernels, which are
+ * APPROXIMATE with a stated tolerance: the dense Gaussian with 16 < d <= 128 (|logp - logp_fp64| <= 1e-5 (1 + |y|^2))
+ * and logistic regression with d = 32 and bf16-representable data (log-density DIFFERENCES between nearby points --
+ * what the accept test sees -- within 2e-3 at N = 10^6; the value itself carries a common offset of up to ~1e-7 N
+ * that cancels in every accept test but is present in the stored log-densities).  Returns KMC_ERR_UNSUPPORTED if the
+ * density has no tensor-core path.
  * "fused_variant" = 2/1: which fused persistent kernel the tensor-core dense Gaussian uses in
  * launch_mode 0 -- 2 (default): matrix pieces resident in TMEM; 1: matrix pieces in shared memory
  * (bit-identical to the three-kernel pipeline of launch_mode 1).
- * Info keys: "tensor_cores" (1 if the tcgen05 path will be used), "batched", "fused_variant". */
+ * Info keys: "tensor_cores" (1 if the tcgen05 path will be used), "tensor_cores_available", "batched",
+ * "fused_variant". */
 int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value);
 int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value);
 /* Batched log-density of nw points (host in, host out).  Used for the initial p0s

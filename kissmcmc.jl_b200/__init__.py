@@ -6,7 +6,7 @@ source (julia/).  Import it as `kissmcmc_b200` (the directory name has a dot in 
 repo-root shim kissmcmc_b200.py registers it).
 """
 from ._lib import (EXCHANGE_PUSH, EXCHANGE_REPLICA, KmcError, MODE_PHILOX, MODE_REPLAY, MULTI_INDEPENDENT, MULTI_SHARDED,
-                   SYMBOLS, LIB_PATH, device_count, lib)
+                   SYMBOLS, LIB_PATH, device_count, lib, trim)
 from .api import (LogDensity, MultiSampler, Sampler, ball_randn, emcee, exponential, gaussian, gaussian_params, logistic, lognormal,
                   make_theta0s, philox4x32_10, rosenbrock, squash_walkers)
 
@@ -25,6 +25,6 @@ def __getattr__(name):
 __all__ = [
     "distributed", "MultiSampler", "EXCHANGE_PUSH", "EXCHANGE_REPLICA", "MULTI_SHARDED", "MULTI_INDEPENDENT", "int_acorr", "acor1d", "auto_window", "eff_samples", "evaluate_convergence",
     "emcee", "make_theta0s", "squash_walkers", "LogDensity", "Sampler", "exponential", "rosenbrock", "gaussian",
-    "gaussian_params", "lognormal", "logistic", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "ball_randn",
+    "gaussian_params", "lognormal", "logistic", "KmcError", "MODE_PHILOX", "MODE_REPLAY", "device_count", "trim", "ball_randn",
     "philox4x32_10", "SYMBOLS", "LIB_PATH", "lib",
 ]

@@ -102,6 +102,11 @@ def check(rc: int) -> None:
         raise KmcError(rc, (lib.kmc_last_error() or b"").decode())
 
 
+def trim() -> None:
+    """Release the library's cached device blocks (buffers of destroyed samplers) back to the driver."""
+    check(lib.kmc_trim())
+
+
 def device_count() -> int:
     n = C.c_int32(0)
     check(lib.kmc_device_count(C.byref(n)))

@@ -111,14 +111,23 @@ def lognormal(mu: float = 0.0, sigma: float = 1.0, device: int = 0) -> LogDensit
     return LogDensity("lognormal", 1, [mu, sigma, math.log(sigma) + 0.5 * math.log(2 * math.pi)], device=device)
 
 
-def logistic(X, y, prior_sigma: float = 10.0, device: int = 0) -> LogDensity:
+def logistic(X, y, prior_sigma: float = 10.0, device: int = 0, tensor_cores: bool = False) -> LogDensity:
     """Bayesian logistic regression (BASELINE.json configs[3]): X [N, d], y [N] in {0, 1}, prior N(0, sigma^2 I).
-    logp(theta) = sum_n (y_n s_n - softplus(s_n)) - |theta|^2 / (2 sigma^2),  s_n = x_n . theta."""
+    logp(theta) = sum_n (y_n s_n - softplus(s_n)) - |theta|^2 / (2 sigma^2),  s_n = x_n . theta.
+
+    Exact FP64 by default.  tensor_cores=True opts in to the tcgen05 kernel (needs d == 32 and every X value
+    bf16-representable, else KmcError): theta split into three bf16 pieces, FP32 accumulation, FP32 softplus.
+    It is APPROXIMATE: log-density differences between nearby points (what the accept test sees) agree with FP64 to
+    2e-3 at N = 10^6 (6e-4 rms); the value itself -- the stored `logdensities` and the initial p0s -- carries a common
+    offset of about +3e-8 per data row (+3e-2 at N = 10^6) that cancels in every accept test."""
     X = np.ascontiguousarray(X, dtype=np.float32)
     y = np.ascontiguousarray(y, dtype=np.float32).ravel()
     assert X.ndim == 2 and y.size == X.shape[0]
     data = np.concatenate([X.ravel(), y])
-    return LogDensity("logistic", X.shape[1], [prior_sigma], data=data, device=device)
+    ld = LogDensity("logistic", X.shape[1], [prior_sigma], data=data, device=device)
+    if tensor_cores:
+        ld.set_option("tensor_cores", 1)
+    return ld
 
 
 # ------------------------------------------------------------------------------------------

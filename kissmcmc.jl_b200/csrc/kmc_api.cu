@@ -14,17 +14,19 @@
 #include <string>
 #include <vector>
 
-#include "../../include/kissmcmc_cuda.h"
-#include "kmc_batched.cuh"
+#include "kmc_internal.cuh"
 #include "kmc_tc.cuh"
 #include "kmc_fused_gauss.cuh"
 #include "kmc_fused_gauss2.cuh"
-#include "kmc_kernels.cuh"
-#include "kmc_push.cuh"
+
+namespace kmc_host {
 
 namespace {
-
 thread_local std::string g_err;
+}
+
+const std::string &last_error() { return g_err; }
+void set_last_error(const std::string &msg) { g_err = msg; }
 
 int32_t fail(int32_t code, const char *fmt, ...) {
     char buf[512];
@@ -36,27 +38,22 @@ int32_t fail(int32_t code, const char *fmt, ...) {
     return code;
 }
 
-#define CU_TRY(expr)                                                                            \
-    do {                                                                                        \
-        cudaError_t e_ = (expr);                                                                \
-        if (e_ != cudaSuccess)                                                                  \
-            return fail(KMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_),   \
-                        __FILE__, __LINE__);                                                    \
-    } while (0)
-
 // ------------------------------------------------------------------ device memory cache
 // cudaMalloc / cudaFree cost milliseconds once pinned host memory and other contexts are
 // mapped; samplers are created and destroyed per emcee() call, so freed blocks are kept in a
 // small per-device cache and reused by exact size.  kmc_trim() releases them.
+namespace {
 struct DevCache {
     std::mutex mu;
     std::multimap<std::pair<int, size_t>, void *> free_blocks;  // (device, bytes) -> ptr
     std::map<void *, std::pair<int, size_t>> live;
     size_t cached_bytes = 0;
-    static constexpr size_t kMaxCached = (size_t)8 << 30;
+    static constexpr size_t kMaxCached = (size_t)2 << 30;  // total kept; kmc_trim() releases everything
+    static constexpr size_t kMaxBlock = (size_t)512 << 20;   // larger blocks (long chains) always go back to the driver
 } g_cache;
+}  // namespace
 
-cudaError_t dev_alloc(void **out, size_t bytes, int device) {
+cudaError_t dev_alloc_raw(void **out, size_t bytes, int device) {
     {
         std::lock_guard<std::mutex> lk(g_cache.mu);
         auto it = g_cache.free_blocks.find({device, bytes});
@@ -84,11 +81,6 @@ cudaError_t dev_alloc(void **out, size_t bytes, int device) {
     return e;
 }
 
-template <typename T>
-cudaError_t dev_alloc(T **out, size_t bytes, int device) {
-    return dev_alloc(reinterpret_cast<void **>(out), bytes, device);
-}
-
 void dev_free(void *p) {
     if (!p) return;
     std::lock_guard<std::mutex> lk(g_cache.mu);
@@ -99,7 +91,7 @@ void dev_free(void *p) {
     }
     const auto key = it->second;
     g_cache.live.erase(it);
-    if (g_cache.cached_bytes + key.second > DevCache::kMaxCached) {
+    if (key.second > DevCache::kMaxBlock || g_cache.cached_bytes + key.second > DevCache::kMaxCached) {
         cudaFree(p);
         return;
     }
@@ -107,77 +99,13 @@ void dev_free(void *p) {
     g_cache.cached_bytes += key.second;
 }
 
-// ------------------------------------------------------------------ kernel registry
-struct Ops {
-    const void *run[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [replay][smem-resident state]
-    const void *run_peer = nullptr;  // general kernel with cross-GPU partner gathers (Philox mode)
-    const void *run_bulk[2] = {nullptr, nullptr};  // [peer] bulk (TMA) general kernel, Philox mode, even D >= 6
-    size_t bulk_smem = 0;
-    const void *run_push = nullptr;  // sharded ensemble with owner-computes pushes (kmc_push.cuh), Philox mode, even D
-    size_t push_smem = 0;
-    size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
-    int block = 0;               // max threads per CTA of the run kernels
-    int min_blocks = 1;          // CTAs per SM the kernels are compiled for
-    int batch = 0;               // 0: fused thread-per-walker kernels; 1: wide Gaussian; 2: logistic (kmc_batched.cuh)
-    const void *eval = nullptr;
-    size_t dn_bytes = 0;
-    int nparams = 0;
-};
-
-template <template <int> class Dn, int D>
-Ops make_ops() {
-    Ops o;
-    o.run[0][0] = (const void *)kmc::emcee_run_kernel<Dn, D, false>;
-    o.run[1][0] = (const void *)kmc::emcee_run_kernel<Dn, D, true>;
-    o.run_peer = (const void *)kmc::emcee_run_kernel<Dn, D, false, true>;
-    if constexpr (D % 2 == 0 && D >= 6) {
-        o.run_bulk[0] = (const void *)kmc::emcee_bulk_kernel<Dn, D, false>;
-        o.run_bulk[1] = (const void *)kmc::emcee_bulk_kernel<Dn, D, true>;
-        o.bulk_smem = (size_t)3 * kmc::kBulkThreads * D * 8 + 16;
-    }
-    if constexpr (D % 2 == 0) {
-        o.run_push = (const void *)kmc::emcee_push_kernel<Dn, D>;
-        o.push_smem = (size_t)3 * kmc::kPushThreads * D * 8 + 2 * sizeof(unsigned long long) +
-                      sizeof(unsigned) * (2 * kmc::kPushSlots * kmc::kPushMaxRanks + kmc::kPushMaxRanks) +
-                      sizeof(unsigned short) * kmc::kPushMaxRounds * kmc::kPushThreads;
-    }
-    if (D <= 4) {  // shared-memory-resident variant for small rows
-        o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;
-        o.run[1][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), true>;
-    }
-    o.smem_per_walker = 8 * D + 8 + 4;
-    o.block = kmc::max_threads<D>();
-    o.min_blocks = kmc::min_blocks<D>();
-    o.eval = (const void *)kmc::density_eval_kernel<Dn, D>;
-    o.dn_bytes = sizeof(Dn<D>);
-    o.nparams = Dn<D>::nparams;
-    return o;
-}
-
-template <template <int> class Dn>
-bool ops_for_dim(int d, Ops &o) {
-    switch (d) {
-        case 2: o = make_ops<Dn, 2>(); return true;
-        case 10: o = make_ops<Dn, 10>(); return true;
-#ifndef KMC_FAST_BUILD  // experiment builds (build/variants/) compile d = 2 and d = 10 only
-        case 1: o = make_ops<Dn, 1>(); return true;
-        case 3: o = make_ops<Dn, 3>(); return true;
-        case 4: o = make_ops<Dn, 4>(); return true;
-        case 5: o = make_ops<Dn, 5>(); return true;
-        case 6: o = make_ops<Dn, 6>(); return true;
-        case 8: o = make_ops<Dn, 8>(); return true;
-        case 12: o = make_ops<Dn, 12>(); return true;
-        case 16: o = make_ops<Dn, 16>(); return true;
-#endif
-        default: return false;
-    }
-}
+namespace {
 
 bool find_ops(int kind, int d, Ops &o) {
     switch (kind) {
-        case kmc::KIND_EXPONENTIAL: return ops_for_dim<kmc::Exponential>(d, o);
+        case kmc::KIND_EXPONENTIAL: return ops_exponential(d, o);
         case kmc::KIND_GAUSSIAN:
-            if (ops_for_dim<kmc::Gaussian>(d, o)) return true;
+            if (ops_gaussian(d, o)) return true;
             if (d > kmc::kWideMaxD) return false;
             o = Ops();
             o.batch = 1;  // dense contraction over the active half
@@ -189,14 +117,8 @@ bool find_ops(int kind, int d, Ops &o) {
             o.batch = 2;
             o.nparams = 1;
             return true;
-        case kmc::KIND_ROSENBROCK:
-            if (d != 2) return false;
-            o = make_ops<kmc::Rosenbrock, 2>();
-            return true;
-        case kmc::KIND_LOGNORMAL:
-            if (d != 1) return false;
-            o = make_ops<kmc::LogNormal, 1>();
-            return true;
+        case kmc::KIND_ROSENBROCK: return ops_rosenbrock(d, o);
+        case kmc::KIND_LOGNORMAL: return ops_lognormal(d, o);
         default: return false;
     }
 }
@@ -211,41 +133,8 @@ int kind_of(const char *name) {
     return -1;
 }
 
-}  // namespace
-
-struct kmc_density_s {
-    int kind = -1;
-    int d = 0;
-    int device = 0;
-    std::vector<double> params;  // also the by-value kernel argument (padded to >= 1 double)
-    Ops ops;
-    double *d_params = nullptr;  // batched plugins: parameters in device memory
-    float *d_X = nullptr, *d_y = nullptr;  // logistic: data
-    long long ndata = 0;
-    // logistic on tcgen05 (kmc_tc.cuh): bf16 copy of X, X^T y, TMA map of X
-    bool tc_ok = false, tc_on = true;
-    __nv_bfloat16 *d_Xbf = nullptr;
-    double *d_xty = nullptr;
-    CUtensorMap mapX;
-    int nsm = 148;
-    // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
-    __nv_bfloat16 *d_Abf = nullptr;
-    int fused_variant = 2;       // dense Gaussian, launch_mode 0: 2 = K2G (matrix in TMEM, default), 1 = K2F (matrix in shared memory)
-    CUtensorMap mapA;
-    double *d_At = nullptr;  // FP64 kernel: A transposed and padded to 128 rows, [d][128]
-};
-
-namespace {
-
 // Batched log-density of npts device-resident points (K4 for the batched plugins; stage 2 of
 // the batched half-step).  `scratch` holds the logistic partial sums ([chunks][npts]).
-struct BatchScratch {
-    double *part = nullptr;
-    size_t bytes = 0;
-    __nv_bfloat16 *pieces = nullptr;  // tcgen05 path: theta split into 3 bf16 pieces [3][wpad][d]
-    size_t pieces_bytes = 0;
-};
-
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -429,67 +318,33 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
 
 }  // namespace
 
-struct kmc_sampler_s {
-    kmc_density_s *dn = nullptr;
-    kmc_emcee_opts opts{};
-    long long nw = 0, nhalf = 0, ns = 0;
-    int d = 0;
-    long long hdone = 0;       // half-steps completed (2 per outer iteration)
-    long long sbeg = 0, scnt = 0;  // shard: positions of each half this sampler updates
-    long long nl = 0;          // walkers this sampler stores chains for (2*scnt)
-    double *x = nullptr, *lp = nullptr, *chain_x = nullptr, *chain_lp = nullptr;
-    unsigned *nacc = nullptr;
-    unsigned long long *barrier = nullptr;
-    unsigned long long bar_base = 0;
-    long long *rp_partner = nullptr;
-    double *rp_z = nullptr, *rp_u = nullptr;
-    long long rp_t0 = 0, rp_niters = 0;
-    cudaStream_t own_stream = nullptr, stream = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
-    long long last_launches = 0;
-    int nsm = 0;
-    unsigned grid = 1, per_cta = 1, block = 32;  // persistent launch geometry
-    size_t smem_bytes = 0;
-    bool use_smem = false;           // owned state is shared-memory resident (emcee_smem_kernel)
-    bool use_bulk = false;           // bulk (TMA) general kernel (emcee_bulk_kernel)
-    unsigned long long *scratch = nullptr;  // 4 x 8 bytes for the statistics kernels
-    kmc::BatchBuf bb{};                     // batched plugins: proposals of the active shard
-    // peer mode
-    int npeers = 0, rank = 0;
-    const double *peer_x[8] = {};
-    unsigned long long *peer_flags[8] = {};
-    unsigned long long *flags = nullptr;    // this rank's flag array [8]
-    unsigned long long epoch = 0;
-    std::vector<void *> ipc_opened;
-    BatchScratch bsc;
-    // local layout of x / lp / nacc: rows held, offset of half 1, offset of this sampler's slice inside a half
-    long long nstate = 0, hoff = 0, loff = 0;
-    // push mode (KMC_EXCHANGE_PUSH, kmc_push.cuh): positions + receive ring + chunk flags in one window allocation
-    bool push = false, attached = false;
-    unsigned char *window = nullptr;
-    size_t win_flags = 0, win_recv = 0, win_x = 0, win_bytes = 0;  // byte offsets inside the window (same on every rank)
-    unsigned long long *task_ctr = nullptr;
-    int G = 1;
-    unsigned chunk = 0, rounds = 0, nchunks = 0, cap = 0, lag = 0;
-    double *peer_recv[8] = {};
-    int share = 1;  // sub-samplers sharing this device (kmc_emcee_create_multi with a repeated ordinal)
-};
-
-namespace {
-// Wire rank r's window (base address as seen from this sampler's device) into the push kernel's peer tables.
-void push_set_peer(kmc_sampler_s *s, int r, unsigned char *base) {
-    s->peer_recv[r] = reinterpret_cast<double *>(base + s->win_recv);
-    s->peer_flags[r] = reinterpret_cast<unsigned long long *>(base + s->win_flags);
-    s->peer_x[r] = reinterpret_cast<const double *>(base + s->win_x);
+cudaError_t eval_on_device(const kmc_density_s &dn, const double *X, long long npts, double *out, BatchScratch &sc,
+                           cudaStream_t st) {
+    if (dn.ops.batch) return launch_batch_logp(dn, X, npts, out, sc, st);
+    long long nwl = npts;
+    void *args[] = {(void *)&X, (void *)&out, &nwl, (void *)dn.params.data()};
+    return cudaLaunchKernel(dn.ops.eval, dim3((unsigned)((npts + 255) / 256)), dim3(256), args, 0, st);
 }
-}  // namespace
+
+void cache_trim() {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    for (auto &kv : g_cache.free_blocks) {
+        cudaSetDevice(kv.first.first);
+        cudaFree(kv.second);
+    }
+    g_cache.free_blocks.clear();
+    g_cache.cached_bytes = 0;
+}
+
+}  // namespace kmc_host
+
+using namespace kmc_host;
 
 extern "C" {
 
 int32_t kmc_version(void) { return 200; }
 
-const char *kmc_last_error(void) { return g_err.c_str(); }
+const char *kmc_last_error(void) { return last_error().c_str(); }
 
 int32_t kmc_device_count(int32_t *count) {
     if (!count) return fail(KMC_ERR_INVALID, "count is NULL");
@@ -504,13 +359,7 @@ int32_t kmc_device_count(int32_t *count) {
 }
 
 int32_t kmc_trim(void) {
-    std::lock_guard<std::mutex> lk(g_cache.mu);
-    for (auto &kv : g_cache.free_blocks) {
-        cudaSetDevice(kv.first.first);
-        cudaFree(kv.second);
-    }
-    g_cache.free_blocks.clear();
-    g_cache.cached_bytes = 0;
+    cache_trim();
     return KMC_OK;
 }
 
@@ -610,6 +459,7 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                     }
                     if (e == cudaSuccess)
                         h->tc_ok = make_map_bf16_k32(&h->mapX, h->d_Xbf, (unsigned long long)N, kmc::tc::BN);
+                    h->tc_on = false;  // exact FP64 kernel by default; opt in with set_option("tensor_cores", 1)
                 }
             }
         }
@@ -625,6 +475,9 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
 int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value) {
     if (!h || !key) return fail(KMC_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "tensor_cores")) {
+        if (value != 0.0 && !h->tc_ok)
+            return fail(KMC_ERR_UNSUPPORTED, "this density has no tcgen05 path (dense Gaussian with 16 < d <= 128; logistic "
+                                             "with d = 32 and bf16-representable data)");
         h->tc_on = value != 0.0;
         return KMC_OK;
     }
@@ -640,6 +493,10 @@ int32_t kmc_density_get_info(kmc_density_t h, const char *key, double *value) {
     if (!h || !key || !value) return fail(KMC_ERR_INVALID, "NULL argument");
     if (!strcmp(key, "tensor_cores")) {
         *value = (h->tc_ok && h->tc_on) ? 1.0 : 0.0;
+        return KMC_OK;
+    }
+    if (!strcmp(key, "tensor_cores_available")) {
+        *value = h->tc_ok ? 1.0 : 0.0;
         return KMC_OK;
     }
     if (!strcmp(key, "batched")) {
@@ -775,7 +632,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         else if (s->nhalf / s->scnt > kmc::kPushMaxRanks) why = "at most 8 ranks";
         else if (density->ops.batch || !density->ops.run_push) why = "a fused (non-batched) plugin with even d";
         else if (opts->mode != KMC_MODE_PHILOX || opts->launch_mode != 0) why = "Philox draws and launch_mode 0";
-        else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxRounds * kmc::kPushThreads) why = "push_chunk in [0, 1024]";
+        else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxChunk) why = "push_chunk in [0, 1024]";
         else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushThreads) why = "push_cap in [0, 256]";
         else if (opts->push_lag < 0) why = "push_lag >= 0";
         if (why) {
@@ -784,12 +641,16 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         }
         s->G = (int)(s->nhalf / s->scnt);
         s->rank = (int)(s->sbeg / s->scnt);
+        // default: a chunk sends kPushThreads/2 rows per destination on average; a ring slot holds 1.5x that
+        // (6 sigma of the binomial hit count at 8 ranks; rows past it are read from the owner directly)
         s->chunk = opts->push_chunk > 0 ? (unsigned)opts->push_chunk
-                                        : (unsigned)std::min<long long>(1024, std::max<long long>(256, 128LL * s->G));
+                                        : (unsigned)std::min<long long>(kmc::kPushMaxChunk,
+                                                                        std::max<long long>(kmc::kPushThreads,
+                                                                                            (kmc::kPushThreads / 2LL) * s->G));
         s->chunk = (unsigned)std::min<long long>(s->chunk, std::max<long long>(s->scnt, 1));
         s->rounds = (s->chunk + kmc::kPushThreads - 1) / kmc::kPushThreads;
         s->nchunks = (unsigned)((s->scnt + s->chunk - 1) / s->chunk);
-        s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : 192u;
+        s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : (unsigned)(3 * kmc::kPushThreads / 4);
     }
     s->nstate = s->push ? 2 * s->scnt : s->nw;
     s->hoff = s->push ? s->scnt : s->nhalf;
@@ -868,9 +729,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         s->grid = (unsigned)(occ * s->nsm);
         s->block = kmc::kPushThreads;
         s->smem_bytes = density->ops.push_smem;
-        s->lag = opts->push_lag > 0 ? (unsigned)opts->push_lag
-                                    : (unsigned)((3 * s->grid / 2 + std::max(1, s->G - 1) - 1) / std::max(1, s->G - 1));
-        s->lag = std::min(s->lag, s->nchunks);
+        s->lag = kmc_host::push_default_lag(s->grid, s->G, s->nchunks, opts->push_lag);
     } else if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
@@ -1353,15 +1212,21 @@ int32_t kmc_emcee_copy_results(kmc_sampler_t s, double *thetas, double *logp, do
             const long long cur = std::min(wc, nl - w0);
             const dim3 blk(32, 8);
             if (thetas) {
-                const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), (unsigned)d);
-                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_x, stage, ns, nl, w0, cur, d);
+                for (long long s0 = 0; s0 < ns; s0 += kmc::kTransposeMaxSamples) {
+                    const long long sc = std::min(kmc::kTransposeMaxSamples, ns - s0);
+                    const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((sc + 31) / 32), (unsigned)d);
+                    kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_x, stage, ns, nl, w0, cur, d, s0);
+                }
                 e = cudaMemcpyAsync(thetas + w0 * ns * d, stage, sizeof(double) * cur * ns * d,
                                     cudaMemcpyDeviceToHost, s->stream);
                 if (e != cudaSuccess) break;
             }
             if (logp) {
-                const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((ns + 31) / 32), 1);
-                kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_lp, stage, ns, nl, w0, cur, 1);
+                for (long long s0 = 0; s0 < ns; s0 += kmc::kTransposeMaxSamples) {
+                    const long long sc = std::min(kmc::kTransposeMaxSamples, ns - s0);
+                    const dim3 grd((unsigned)((cur + 31) / 32), (unsigned)((sc + 31) / 32), 1);
+                    kmc::chain_transpose_kernel<<<grd, blk, 0, s->stream>>>(s->chain_lp, stage, ns, nl, w0, cur, 1, s0);
+                }
                 e = cudaMemcpyAsync(logp + w0 * ns, stage, sizeof(double) * cur * ns, cudaMemcpyDeviceToHost,
                                     s->stream);
             }
@@ -1421,171 +1286,6 @@ int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64
         std::vector<unsigned> h(nst);
         CU_TRY(cudaMemcpy(h.data(), s->nacc, sizeof(unsigned) * nst, cudaMemcpyDeviceToHost));
         for (long long w = 0; w < nst; ++w) naccept[w] = h[w];
-    }
-    return KMC_OK;
-}
-
-// ------------------------------------------------------------------ library-owned multi-GPU (single process)
-}  // extern "C"
-
-struct kmc_multi_s {
-    int mode = KMC_MULTI_SHARDED;
-    long long nw = 0;  // walkers per ensemble
-    int d = 0;
-    std::vector<kmc_sampler_s *> subs;
-};
-
-extern "C" {
-
-int32_t kmc_multi_destroy(kmc_multi_t m) {
-    if (!m) return KMC_OK;
-    for (auto *s : m->subs)  // nobody tears its window down while a peer's kernel may still write into it
-        if (s) {
-            cudaSetDevice(s->opts.device);
-            cudaStreamSynchronize(s->stream);
-        }
-    for (auto *s : m->subs) kmc_emcee_destroy(s);
-    delete m;
-    return KMC_OK;
-}
-
-int32_t kmc_emcee_create_multi(const kmc_density_t *densities, const double *theta0s, int64_t nwalkers, int32_t d,
-                               const kmc_emcee_opts *opts, const int32_t *devices, int32_t ndev, int32_t mode,
-                               kmc_multi_t *out) {
-    if (!out) return fail(KMC_ERR_INVALID, "out is NULL");
-    *out = nullptr;
-    if (!densities || !theta0s || !opts || !devices) return fail(KMC_ERR_INVALID, "NULL argument");
-    if (ndev < 1 || ndev > kmc::kPushMaxRanks) return fail(KMC_ERR_INVALID, "ndev must be in [1, 8]");
-    if (mode != KMC_MULTI_SHARDED && mode != KMC_MULTI_INDEPENDENT) return fail(KMC_ERR_INVALID, "unknown mode %d", mode);
-    for (int r = 0; r < ndev; ++r)
-        if (!densities[r]) return fail(KMC_ERR_INVALID, "densities[%d] is NULL", r);
-    if (mode == KMC_MULTI_SHARDED && (nwalkers < 2 || (nwalkers & 1) || (nwalkers / 2) % ndev))
-        return fail(KMC_ERR_INVALID, "nwalkers/2 must be a multiple of the number of devices");
-    auto *m = new kmc_multi_s;
-    m->mode = mode;
-    m->nw = nwalkers;
-    m->d = d;
-    m->subs.assign(ndev, nullptr);
-    auto bail = [&](int32_t rc) {
-        const std::string keep = g_err;
-        kmc_multi_destroy(m);
-        g_err = keep;
-        return rc;
-    };
-    const long long S = nwalkers / 2 / ndev;
-    for (int r = 0; r < ndev; ++r) {
-        kmc_emcee_opts o = *opts;
-        o.device = devices[r];
-        if (mode == KMC_MULTI_SHARDED) {
-            o.exchange = KMC_EXCHANGE_PUSH;
-            o.shard_begin = r * S;
-            o.shard_count = S;
-            o.launch_mode = 0;
-        } else {  // independent ensembles: disjoint walker ids => disjoint Philox streams
-            o.exchange = KMC_EXCHANGE_REPLICA;
-            o.shard_begin = o.shard_count = 0;
-            o.walker_id_base = opts->walker_id_base + (int64_t)r * nwalkers;
-        }
-        const double *th = mode == KMC_MULTI_SHARDED ? theta0s : theta0s + (size_t)r * nwalkers * d;
-        const int32_t rc = kmc_emcee_create(densities[r], th, nwalkers, d, &o, &m->subs[r]);
-        if (rc != KMC_OK) return bail(rc);
-    }
-    if (mode == KMC_MULTI_SHARDED) {
-        for (int a = 0; a < ndev; ++a) {
-            kmc_sampler_s *sa = m->subs[a];
-            int share = 0;
-            for (int b = 0; b < ndev; ++b) share += devices[b] == devices[a] ? 1 : 0;
-            sa->share = share;  // sub-samplers of one GPU must all be co-resident: split the CTA slots
-            sa->grid = std::max(1u, sa->grid / (unsigned)share);
-            sa->lag = std::min(sa->nchunks, (unsigned)((3 * sa->grid / 2 + std::max(1, ndev - 1) - 1) / std::max(1, ndev - 1)));
-            if (opts->push_lag > 0) sa->lag = std::min(sa->nchunks, (unsigned)opts->push_lag);
-            if (cudaSetDevice(devices[a]) != cudaSuccess) return bail(fail(KMC_ERR_CUDA, "cudaSetDevice(%d) failed", devices[a]));
-            for (int b = 0; b < ndev; ++b) {
-                if (devices[b] != devices[a]) {
-                    int can = 0;
-                    cudaDeviceCanAccessPeer(&can, devices[a], devices[b]);
-                    if (!can) return bail(fail(KMC_ERR_CUDA, "device %d cannot access device %d's memory", devices[a], devices[b]));
-                    const cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
-                    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
-                        return bail(fail(KMC_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", devices[a], devices[b],
-                                         cudaGetErrorString(e)));
-                    cudaGetLastError();
-                }
-                push_set_peer(sa, b, m->subs[b]->window);
-            }
-            sa->attached = true;
-        }
-    }
-    *out = m;
-    return KMC_OK;
-}
-
-int32_t kmc_multi_run(kmc_multi_t m, int64_t niters) {
-    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
-    for (auto *s : m->subs) {  // asynchronous launches: the devices' kernels synchronise among themselves
-        const int32_t rc = kmc_emcee_run(s, niters);
-        if (rc != KMC_OK) return rc;
-    }
-    return KMC_OK;
-}
-
-int32_t kmc_multi_sync(kmc_multi_t m) {
-    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
-    for (auto *s : m->subs) {
-        const int32_t rc = kmc_emcee_sync(s);
-        if (rc != KMC_OK) return rc;
-    }
-    return KMC_OK;
-}
-
-int32_t kmc_multi_last_run_ms(kmc_multi_t m, double *ms) {
-    if (!m || !ms) return fail(KMC_ERR_INVALID, "NULL argument");
-    *ms = 0.0;
-    for (auto *s : m->subs) {
-        double v = 0.0;
-        const int32_t rc = kmc_emcee_last_run_ms(s, &v, nullptr);
-        if (rc != KMC_OK) return rc;
-        *ms = std::max(*ms, v);
-    }
-    return KMC_OK;
-}
-
-int32_t kmc_multi_shape(kmc_multi_t m, int64_t *ns, int64_t *nwalkers_out) {
-    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
-    if (ns) *ns = m->subs[0]->ns;
-    if (nwalkers_out) *nwalkers_out = m->mode == KMC_MULTI_SHARDED ? m->nw : m->nw * (long long)m->subs.size();
-    return KMC_OK;
-}
-
-int32_t kmc_multi_copy_results(kmc_multi_t m, double *thetas, double *logp, double *accept_ratio) {
-    if (!m) return fail(KMC_ERR_INVALID, "NULL handle");
-    const long long ns = m->subs[0]->ns, nw = m->nw;
-    const int d = m->d, ndev = (int)m->subs.size();
-    if (m->mode == KMC_MULTI_INDEPENDENT) {
-        for (int r = 0; r < ndev; ++r) {
-            const int32_t rc = kmc_emcee_copy_results(m->subs[r], thetas ? thetas + (size_t)r * nw * ns * d : nullptr,
-                                                      logp ? logp + (size_t)r * nw * ns : nullptr,
-                                                      accept_ratio ? accept_ratio + (size_t)r * nw : nullptr);
-            if (rc != KMC_OK) return rc;
-        }
-        return KMC_OK;
-    }
-    // sharded: sub r returns its slice of half 0 then of half 1 ([2S] walkers); global order = all slices of half 0, then of half 1
-    const long long S = nw / 2 / ndev;
-    std::vector<double> th, lp, ar;
-    if (thetas) th.resize((size_t)2 * S * ns * d);
-    if (logp) lp.resize((size_t)2 * S * ns);
-    if (accept_ratio) ar.resize((size_t)2 * S);
-    for (int r = 0; r < ndev; ++r) {
-        const int32_t rc = kmc_emcee_copy_results(m->subs[r], thetas ? th.data() : nullptr, logp ? lp.data() : nullptr,
-                                                  accept_ratio ? ar.data() : nullptr);
-        if (rc != KMC_OK) return rc;
-        for (int b = 0; b < 2; ++b) {
-            const size_t dst = (size_t)b * (nw / 2) + (size_t)r * S, src = (size_t)b * S;
-            if (thetas) memcpy(thetas + dst * ns * d, th.data() + src * ns * d, sizeof(double) * S * ns * d);
-            if (logp) memcpy(logp + dst * ns, lp.data() + src * ns, sizeof(double) * S * ns);
-            if (accept_ratio) memcpy(accept_ratio + dst, ar.data() + src, sizeof(double) * S);
-        }
     }
     return KMC_OK;
 }

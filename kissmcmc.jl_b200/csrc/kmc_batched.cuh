@@ -27,7 +27,7 @@ struct BatchBuf {
 
 // One warp per active walker; lanes stride over the components (coalesced row access).
 template <bool REPLAY>
-__global__ void __launch_bounds__(256) propose_kernel(const RunParams p, const BatchBuf b, long long h, int d) {
+static __global__ void __launch_bounds__(256) propose_kernel(const RunParams p, const BatchBuf b, long long h, int d) {
     const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const unsigned W = p.shard_end - p.shard_begin;
     if (w >= W) return;
@@ -47,7 +47,7 @@ __global__ void __launch_bounds__(256) propose_kernel(const RunParams p, const B
 }
 
 template <bool REPLAY>
-__global__ void __launch_bounds__(256) accept_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+static __global__ void __launch_bounds__(256) accept_kernel(const RunParams p, const BatchBuf b, long long h, int d,
                                                      long long n, int store, long long sidx) {
     const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const unsigned W = p.shard_end - p.shard_begin;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) accept_kernel(const RunParams p, const Ba
 // bits -- only for accepted walkers (and for the chain store).  Saves the Y write, the Y read of a
 // separate split kernel and the Y read of accept: ~230 MB -> ~120 MB per half-step at d = 100.
 template <bool REPLAY>
-__global__ void __launch_bounds__(256) propose_pieces_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+static __global__ void __launch_bounds__(256) propose_pieces_kernel(const RunParams p, const BatchBuf b, long long h, int d,
                                                              const double *__restrict__ mu,
                                                              __nv_bfloat16 *__restrict__ pieces, long long wpad) {
     const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(256) propose_pieces_kernel(const RunParams p, 
 }
 
 template <bool REPLAY>
-__global__ void __launch_bounds__(256) accept_recompute_kernel(const RunParams p, const BatchBuf b, long long h, int d,
+static __global__ void __launch_bounds__(256) accept_recompute_kernel(const RunParams p, const BatchBuf b, long long h, int d,
                                                                long long n, int store, long long sidx) {
     const unsigned w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     const unsigned W = p.shard_end - p.shard_begin;
@@ -170,7 +170,7 @@ constexpr int kWidePts = 4;        // points per warp per pass (register tile: 4
 // centred coordinate (broadcast 32-byte read of the 4 points) feeds 4 FMAs: 16 DFMA per 6 LDS -- the
 // FP64 pipe, not the LSU, is the bound.  At is padded to 128 rows of zeros (no masks in the loop).
 // Accumulation order per (point, row) is j = 0..d-1 with FMA, then rows in order, then the xor tree.
-__global__ void __launch_bounds__(kWideThreads, 1) gaussian_wide_logp_kernel(const double *__restrict__ X,
+static __global__ void __launch_bounds__(kWideThreads, 1) gaussian_wide_logp_kernel(const double *__restrict__ X,
                                                                               double *__restrict__ out, long long npts,
                                                                               int d, const double *__restrict__ prm,
                                                                               const double *__restrict__ At_g) {
@@ -234,7 +234,7 @@ constexpr int kLogitTile = 32;
 __device__ __forceinline__ double softplus64(double s) { return fmax(s, 0.0) + log1p(exp(-fabs(s))); }
 
 // part[chunk][pt] partial sums, then a fixed-order finish: bit-reproducible run to run.
-__global__ void __launch_bounds__(256) logistic_logp_kernel(const double *__restrict__ TH, double *__restrict__ part,
+static __global__ void __launch_bounds__(256) logistic_logp_kernel(const double *__restrict__ TH, double *__restrict__ part,
                                                             long long npts, int d, const float *__restrict__ X,
                                                             const float *__restrict__ yv, long long N,
                                                             long long rows_per_chunk) {
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256) logistic_logp_kernel(const double *__rest
     }
 }
 
-__global__ void logistic_finish_kernel(const double *__restrict__ TH, const double *__restrict__ part,
+static __global__ void logistic_finish_kernel(const double *__restrict__ TH, const double *__restrict__ part,
                                        double *__restrict__ out, long long npts, int d, int nchunks, double inv2s2) {
     const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (pt >= npts) return;

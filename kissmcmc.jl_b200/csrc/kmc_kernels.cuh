@@ -242,7 +242,7 @@ __device__ __forceinline__ void cross_gpu_barrier(const RunParams &p, unsigned l
 // ------------------------------------------------------------------ general kernel
 // Owned state stays in L2/HBM; any ensemble size.  U walkers in flight per thread.
 template <template <int> class Dn, int D, bool REPLAY, bool PEER = false>
-__global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_kernel(const RunParams p,
+static __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emcee_run_kernel(const RunParams p,
                                                                                     const Dn<D> dn) {
     constexpr int U = in_flight<D>();
     const unsigned shard_size = p.shard_end - p.shard_begin;
@@ -414,7 +414,7 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsig
 }
 
 template <template <int> class Dn, int D, bool PEER>
-__global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
+static __global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
     static_assert(D % 2 == 0, "rows must be multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     constexpr unsigned T = kBulkThreads, ROWB = D * 8;
@@ -585,7 +585,7 @@ __device__ __forceinline__ void sts_u32(unsigned a, unsigned v) {
 }
 
 template <template <int> class Dn, int D, bool REPLAY>
-__global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
+static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_kernel(const RunParams p, const Dn<D> dn) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const unsigned nthr = blockDim.x;
     const unsigned L = 2 * p.per_cta;
@@ -709,7 +709,7 @@ __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_kernel(con
 
 // K4: batched log-density (initial p0s, src/samplers.jl:209; make_theta0s, :334-338).
 template <template <int> class Dn, int D>
-__global__ void __launch_bounds__(256) density_eval_kernel(const double *__restrict__ x, double *__restrict__ out,
+static __global__ void __launch_bounds__(256) density_eval_kernel(const double *__restrict__ x, double *__restrict__ out,
                                                            long long nw, const Dn<D> dn) {
     const long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (w >= nw) return;
@@ -719,13 +719,14 @@ __global__ void __launch_bounds__(256) density_eval_kernel(const double *__restr
 }
 
 // Chain store is sample-major on the device ([ns][nw][D]); the ABI wants walker-major
-// ([nw][ns][D]).  Transposes walkers [w0, w0+wc) into a staging buffer.
-__global__ void chain_transpose_kernel(const double *__restrict__ in, double *__restrict__ out, long long ns,
-                                       long long nw, long long w0, long long wc, int d) {
+// ([nw][ns][D]).  Transposes walkers [w0, w0+wc), samples [s0, s0 + 32*gridDim.y) into a staging buffer.
+constexpr long long kTransposeMaxSamples = 65535LL * 32;  // gridDim.y limit: longer chains take several launches
+static __global__ void chain_transpose_kernel(const double *__restrict__ in, double *__restrict__ out, long long ns,
+                                       long long nw, long long w0, long long wc, int d, long long s0) {
     __shared__ double tile[32][33];
     // element (s, w) is a d-vector; handle one component per blockIdx.z
     const int c = blockIdx.z;
-    const long long wb = (long long)blockIdx.x * 32, sb = (long long)blockIdx.y * 32;
+    const long long wb = (long long)blockIdx.x * 32, sb = s0 + (long long)blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const long long s = sb + r, w = wb + threadIdx.x;
         if (s < ns && w < wc) tile[r][threadIdx.x] = in[(s * nw + (w0 + w)) * d + c];
@@ -740,7 +741,7 @@ __global__ void chain_transpose_kernel(const double *__restrict__ in, double *__
 // Posterior moments of the stored chain on the device (the squash_walkers + mean/var reduction
 // of src/samplers.jl:372-428 + test/runtests.jl:36-43 without copying the chain to the host):
 // per component, sum and sum of squares of (x - shift), shift = the first stored sample.
-__global__ void __launch_bounds__(256) chain_moments_kernel(const double *__restrict__ chain, long long nrows, int d,
+static __global__ void __launch_bounds__(256) chain_moments_kernel(const double *__restrict__ chain, long long nrows, int d,
                                                             double *__restrict__ sums /* [2][d] */) {
     extern __shared__ double sh[];  // [2][d]
     for (int c = threadIdx.x; c < 2 * d; c += blockDim.x) sh[c] = 0.0;
@@ -757,7 +758,7 @@ __global__ void __launch_bounds__(256) chain_moments_kernel(const double *__rest
 }
 
 // K5: accept-counter statistics of the progress display (src/samplers.jl:276-278).
-__global__ void nacc_sum_kernel(const unsigned *__restrict__ nacc, long long nw, unsigned long long *sum) {
+static __global__ void nacc_sum_kernel(const unsigned *__restrict__ nacc, long long nw, unsigned long long *sum) {
     unsigned long long s = 0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x)
         s += nacc[i];
@@ -765,7 +766,7 @@ __global__ void nacc_sum_kernel(const unsigned *__restrict__ nacc, long long nw,
     if ((threadIdx.x & 31) == 0 && s) atomicAdd(sum, s);
 }
 
-__global__ void nacc_moment_kernel(const unsigned *__restrict__ nacc, long long nw, double mean, double thresh,
+static __global__ void nacc_moment_kernel(const unsigned *__restrict__ nacc, long long nw, double mean, double thresh,
                                    double *ssq, unsigned long long *outl) {
     double s = 0.0;
     unsigned long long o = 0;

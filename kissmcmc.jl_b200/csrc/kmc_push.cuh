@@ -14,7 +14,7 @@
 //                   hits in my passive shard are gathered (one bulk copy per row), PACKED in walker order in shared
 //                   memory and sent as ONE bulk store (cp.async.bulk shared -> peer global, up to cap*8D bytes) into
 //                   dest's receive ring slot (half-step parity, source = me, chunk c); when the store has completed,
-//                   the "chunk ready" flag (source, c) in dest's memory is set to h+1 (st.release.sys).
+//                   the "chunk ready" flag (source, c) in dest's memory is set to h+1 (release at system scope).
 //   update(c)       the stretch-move step of my chunk c: the same draws give every walker's owner and its rank among
 //                   the chunk's walkers with that owner = its row in the packed message; waits for the G-1 chunk
 //                   flags, then runs the bulk kernel's group loop (kmc_kernels.cuh, emcee_bulk_kernel) with the
@@ -25,10 +25,18 @@
 // there is no cross-GPU barrier at all -- a consumer starts as soon as ITS chunk's rows have landed -- and one local
 // grid barrier per half-step (random rows of the whole shard are read by the next half-step's pushes).
 //
+// Nothing a push does is waited for where it is issued (thread 0 is the CTA's "sender"):
+//   * the row gathers of push t land while the CTA enumerates its NEXT task; the sender issues the bulk store of push t
+//     at that task's service point (after its enumeration);
+//   * the store's completion is not waited for either: a flag is published (system-scope fence + store; kPushBatch
+//     flags per fence) at a later service point, once `cp.async.bulk.wait_group 1` says its store is complete -- or
+//     when the CTA is about to block on somebody else's flag, or at the end of the half-step.
+//
 // Why there is no deadlock: give push(c, *) level c and update(c) level c + lag + 1/2.  Tasks are taken in level order
 // by co-resident CTAs (cooperative launch), a task only ever waits for strictly lower levels of the same half-step on
-// other GPUs, and pushes wait for nothing.  Why two ring parities suffice: rank q can only push for half-step h+2 after
-// it finished update h+1, which needs every rank's pushes of h+1, which a rank sends only after its update h.
+// other GPUs, pushes wait for nothing, and a CTA never blocks while it holds an unpublished flag.  Why two ring
+// parities suffice: rank q can only push for half-step h+2 after it finished update h+1, which needs every rank's
+// pushes of h+1, which a rank sends only after its update h.
 //
 // Exactness: every walker-step is the same arithmetic on the same draws as the single-GPU kernels, so a sharded run is
 // bit-identical to the single-GPU run of the same ensemble (tests/test_gpu_push.py).
@@ -37,12 +45,24 @@
 
 namespace kmc {
 
-constexpr int kPushThreads = 256;
-constexpr int kPushMaxRounds = 4;  // chunk <= 4 * 256 walkers
+#ifndef KMC_PUSH_THREADS
+#define KMC_PUSH_THREADS 256
+#endif
+#ifndef KMC_PUSH_CTAS
+#define KMC_PUSH_CTAS 3
+#endif
+constexpr int kPushThreads = KMC_PUSH_THREADS;
+constexpr int kPushWarps = kPushThreads / 32;
+constexpr int kPushMaxChunk = 1024;
+constexpr int kPushMaxRounds = kPushMaxChunk / kPushThreads;  // rounds of T walkers per chunk
 constexpr int kPushMaxRanks = 8;
-constexpr int kPushSlots = 32;     // (round, warp) slots of a chunk: 4 rounds x 8 warps
-static_assert(kPushSlots * kPushMaxRanks == kPushThreads, "one thread zeroes one counter");
-static_assert(kPushMaxRounds * (kPushThreads / 32) == kPushSlots, "slots = rounds x warps = one warp's lanes");
+constexpr int kPushSlots = 32;  // (round, warp) slots of a chunk = one warp's lanes (prefix by shuffles)
+constexpr int kPushFifo = 8;    // flags whose store is issued but which are not published yet
+#ifndef KMC_PUSH_BATCH
+#define KMC_PUSH_BATCH 1
+#endif
+constexpr unsigned kPushBatch = KMC_PUSH_BATCH;  // flags published per system-scope fence (1: as soon as the store is complete)
+static_assert(kPushMaxRounds * kPushWarps == kPushSlots, "slots = rounds x warps = one warp's lanes");
 
 struct PushParams {
     double *recv;               // local receive ring [2 parities][G sources][nchunks][cap][D]
@@ -54,11 +74,29 @@ struct PushParams {
     unsigned S;        // shard size: positions of each half per rank
     unsigned G, rank;  // ranks, my rank
     unsigned chunk;    // walkers per chunk (<= 1024)
-    unsigned rounds;   // ceil(chunk / 256)
+    unsigned rounds;   // ceil(chunk / kPushThreads)
     unsigned nchunks;  // ceil(S / chunk)
-    unsigned cap;      // rows per ring slot (<= 256)
+    unsigned cap;      // rows per ring slot (<= kPushThreads)
     unsigned lag;      // update(c) follows push(c + lag, *)
 };
+
+// The sender's state: touched by thread 0 only, kept in shared memory so that it costs the other 255 threads no registers.
+struct PushSender {
+    double *dst;                     // the push whose gathers are in flight and whose store is not issued yet
+    unsigned long long *flag;
+    unsigned pending, buf, bytes;
+    unsigned gphase;                 // bit b: phase of gbar[b]
+    unsigned ncommit;                // bulk store groups committed so far
+    unsigned fhead, ftail;           // fifo[fhead..ftail): flags of issued stores that are not published yet
+    unsigned pad;
+};
+
+// Dynamic shared memory of the kernel for rows of D doubles.
+constexpr size_t push_smem_bytes(int D) {
+    return (size_t)3 * kPushThreads * D * 8 + sizeof(PushSender) + sizeof(unsigned long long) * (4 + kPushFifo) +
+           sizeof(unsigned) * (2 * kPushSlots * kPushMaxRanks + kPushMaxRanks + kPushFifo) +
+           sizeof(unsigned short) * kPushMaxChunk;
+}
 
 // The partner draw alone (src/samplers.jl:250): the owner side of a push needs nothing else of the walker-step.
 __device__ __forceinline__ unsigned partner_pos(const RunParams &p, long long h, unsigned i) {
@@ -72,75 +110,110 @@ __device__ __forceinline__ unsigned partner_pos(const RunParams &p, long long h,
     return hi;  // position inside the passive half
 }
 
-__device__ __forceinline__ void flag_publish(unsigned long long *flag, unsigned long long v) {
-    asm volatile("fence.proxy.async;" ::: "memory");  // the bulk store's writes (async proxy) before the flag (generic proxy)
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(v) : "memory");
+__device__ __forceinline__ unsigned long long flag_peek(const unsigned long long *flag) {
+    unsigned long long cur;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+    return cur;
 }
 
 __device__ __forceinline__ void flag_wait(const unsigned long long *flag, unsigned long long v) {
-    unsigned long long cur;
     long long t0 = 0;
     unsigned spins = 0;
-    do {
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
-        if (cur < v && (++spins & 0x3FFu) == 0) {  // watchdog (~10 s): a missing peer must not hang the GPU
+    while (flag_peek(flag) < v) {
+        if ((++spins & 0x3FFu) == 0) {  // watchdog (~10 s): a missing peer must not hang the GPU
             if (t0 == 0) t0 = clock64();
             else if (clock64() - t0 > 20000000000LL) __trap();
         }
-    } while (cur < v);
+    }
 }
 
 template <template <int> class Dn, int D>
-__global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunParams p, const PushParams q,
-                                                                      const Dn<D> dn) {
+__global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel(const RunParams p, const PushParams q,
+                                                                                  const Dn<D> dn) {
     static_assert(D % 2 == 0, "rows must be multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char push_smem[];
     constexpr unsigned T = kPushThreads, ROWB = D * 8;
     double *buf = reinterpret_cast<double *>(push_smem);  // [2][T][D]: own rows of an update group | packed rows of a push
     double *xpart = buf + 2 * T * D;                      // [T][D] partner rows of an update group
-    unsigned long long *ldbar = reinterpret_cast<unsigned long long *>(xpart + T * D);
-    unsigned long long *next_slot = ldbar + 1;            // broadcast of the next task id
-    unsigned *cnt = reinterpret_cast<unsigned *>(ldbar + 2);  // [kPushSlots][kPushMaxRanks] hits per (round, warp) and owner
-    unsigned *pre = cnt + kPushSlots * kPushMaxRanks;         // exclusive prefix of cnt over the slots, per owner
-    unsigned *tot = pre + kPushSlots * kPushMaxRanks;         // [kPushMaxRanks] totals
-    unsigned short *rowidx = reinterpret_cast<unsigned short *>(tot + kPushMaxRanks);  // [chunk] row in the packed message
+    PushSender *snd = reinterpret_cast<PushSender *>(xpart + T * D);
+    unsigned long long *ldbar = reinterpret_cast<unsigned long long *>(snd + 1);        // loads of an update group
+    unsigned long long *gbar = ldbar + 1;                 // [2] row gathers of the push that owns buf[b]
+    unsigned long long *next_slot = ldbar + 3;            // broadcast of the next task id
+    unsigned long long **fifo = reinterpret_cast<unsigned long long **>(ldbar + 4);  // [kPushFifo] sender's flag queue
+    unsigned *cnt = reinterpret_cast<unsigned *>(ldbar + 4 + kPushFifo);  // [kPushSlots][kPushMaxRanks] hits per slot, owner
+    unsigned *pre = cnt + kPushSlots * kPushMaxRanks;     // exclusive prefix of cnt over the slots, per owner
+    unsigned *tot = pre + kPushSlots * kPushMaxRanks;     // [kPushMaxRanks] totals
+    unsigned *fidx = tot + kPushMaxRanks;                 // [kPushFifo] commit index of the store behind fifo[k]
+    unsigned short *rowidx = reinterpret_cast<unsigned short *>(fidx + kPushFifo);  // [chunk] row in the packed message
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned S = q.S, me = q.rank, G = q.G;
     const unsigned NT = (q.nchunks + q.lag) * G;  // tasks per half-step
-    if (tid == 0) kbar_init(ldbar, 1);
+    if (tid == 0) {
+        kbar_init(ldbar, 1);
+        kbar_init(gbar, 1);
+        kbar_init(gbar + 1, 1);
+        snd->pending = snd->gphase = snd->ncommit = snd->fhead = snd->ftail = 0u;
+    }
     __syncthreads();
     unsigned ldphase = 0, unit = 0;
-    // thread 0: chunk flags of the last two store units, published once their bulk store has completed
-    // (scalars selected by parity, not arrays: dynamic indexing would put them in local memory)
-    unsigned long long *pf0 = nullptr, *pf1 = nullptr;
-    unsigned long long pv0 = 0, pv1 = 0;
-    auto publish_pending = [&](bool first, bool second) {
-        if (first && pf0) {
-            flag_publish(pf0, pv0);
-            pf0 = nullptr;
-        }
-        if (second && pf1) {
-            flag_publish(pf1, pv1);
-            pf1 = nullptr;
-        }
-    };
 
-    // A "unit" is a push task or an update group: it owns buf[unit & 1] and commits exactly one bulk store group.
-    // Its buffer was last used two units ago: all but the latest store group must be complete (which also lets the
-    // flag of the unit two back go out), then everyone may overwrite the buffer (and xpart).
-    auto unit_begin = [&]() -> double * {
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-            publish_pending((unit & 1) == 0, (unit & 1) == 1);
+    // ------------------------------------------------------------------ the sender (thread 0)
+    // A "unit" is a push task or an update group: it owns buf[unit & 1] and commits exactly ONE bulk store group
+    // (a push commits it one service point later).  snd_*: the push whose gathers are in flight and whose store is not
+    // issued yet.  fifo[fhead..ftail): flags of issued stores; fidx[k]: the commit index of the store behind fifo[k].
+    auto commit = [&]() {
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        snd->ncommit += 1;
+    };
+    // issue the bulk store of the pending push (its gathers have landed by now: they were issued a task ago)
+    auto service = [&]() {
+        if (!snd->pending) return;
+        const unsigned sb = snd->buf;
+        kbar_wait(gbar + sb, (snd->gphase >> sb) & 1u);
+        snd->gphase ^= 1u << sb;
+        if (snd->bytes) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(snd->dst),
+                         "r"((unsigned)__cvta_generic_to_shared(buf + (size_t)sb * T * D)), "r"(snd->bytes)
+                         : "memory");
         }
-        __syncthreads();
-        return buf + (size_t)(unit & 1) * T * D;
+        commit();
+        const unsigned ft = snd->ftail;
+        fifo[ft % kPushFifo] = snd->flag;
+        fidx[ft % kPushFifo] = snd->ncommit;
+        snd->ftail = ft + 1;
+        snd->pending = 0;
     };
+    // publish the flags whose stores are complete: one system-scope fence for the whole batch
+    auto publish = [&](bool all, unsigned long long ready) {
+        unsigned fhead = snd->fhead;
+        const unsigned ftail = snd->ftail, ncommit = snd->ncommit;
+        if (fhead == ftail) return;
+        unsigned upto = fhead;
+        if (all) {
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+            upto = ftail;
+        } else {
+            while (upto != ftail && fidx[upto % kPushFifo] + 1 <= ncommit) ++upto;  // complete after wait_group 1
+            if (upto - fhead < kPushBatch && ftail - fhead < kPushFifo - 1) return;  // batch not worth a fence yet
+            if (upto == fhead) {  // queue full of young stores: wait for all of them
+                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                upto = ftail;
+            } else {
+                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            }
+        }
+        asm volatile("fence.proxy.async;" ::: "memory");  // the bulk stores' writes (async proxy) before the flags
+        asm volatile("fence.acq_rel.sys;" ::: "memory");
+        for (; fhead != upto; ++fhead)
+            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fifo[fhead % kPushFifo]), "l"(ready) : "memory");
+        snd->fhead = fhead;
+    };
+    // before buf[unit & 1] is overwritten: the store that read it two units ago has finished reading
+    auto buffer_free = [&]() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); };
 
-    auto grab = [&]() -> unsigned long long {  // thread 0 only
-        return atomicAdd(q.task_ctr, 1ULL);
-    };
+    auto grab = [&]() -> unsigned long long { return atomicAdd(q.task_ctr, 1ULL); };  // thread 0 only
 
 #ifdef KMC_PUSH_PROF  // thread 0's cycles per phase (experiment builds only)
     long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc0 = clock64();
@@ -175,19 +248,18 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
             if (slot + 1 < G) {
                 // ------------------------------------------------------------ push(c, dest)
                 if (c < q.nchunks) {
+                    PUSH_TICK(9);
                     const unsigned dest = (me + 1 + slot) % G;
                     const unsigned i0 = dest * S + c * q.chunk;  // first active walker (position in its half) of the chunk
                     const unsigned lim = min(q.chunk, S - c * q.chunk);
-                    PUSH_TICK(9);
-                    double *pk = unit_begin();
-                    PUSH_TICK(0);
+                    const unsigned b = unit & 1;
+                    double *pk = buf + (size_t)b * T * D;
                     unsigned lrow[kPushMaxRounds], rk[kPushMaxRounds];
-                    if (tid < kPushSlots) cnt[tid] = 0u;
-                    __syncthreads();
 #pragma unroll
                     for (int g = 0; g < kPushMaxRounds; ++g) {
                         lrow[g] = 0xFFFFFFFFu;
                         rk[g] = 0;
+                        unsigned nh = 0;
                         if (g < (int)q.rounds) {
                             const unsigned off = g * T + tid;
                             bool hit = false;
@@ -196,12 +268,14 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
                                 hit = pl < S;
                                 if (hit) lrow[g] = pl;
                             }
-                            const unsigned b = __ballot_sync(0xffffffffu, hit);
-                            rk[g] = __popc(b & ((1u << lane) - 1u));
-                            if (lane == 0) cnt[g * 8 + warp] = __popc(b);
+                            const unsigned bl = __ballot_sync(0xffffffffu, hit);
+                            rk[g] = __popc(bl & ((1u << lane) - 1u));
+                            nh = __popc(bl);
                         }
+                        if (lane == 0) cnt[g * kPushWarps + warp] = nh;
                     }
                     __syncthreads();
+                    PUSH_TICK(1);
                     if (warp == 0) {
                         const unsigned v = cnt[lane];
                         unsigned incl = v;
@@ -212,79 +286,62 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
                         }
                         pre[lane] = incl - v;
                         if (lane == 31) tot[0] = incl;
+                        if (lane == 0) {  // the sender: previous push goes out, this unit's buffer is free, flags in batches
+                            service();
+                            buffer_free();
+                            publish(false, ready);
+                        }
                     }
                     __syncthreads();
+                    PUSH_TICK(0);
                     const unsigned nsend = min(tot[0], q.cap);
-                    PUSH_TICK(1);
-                    if (tid == 0) kbar_expect_tx(ldbar, nsend * ROWB);
+                    if (tid == 0) kbar_expect_tx(gbar + b, nsend * ROWB);
 #pragma unroll
                     for (int g = 0; g < kPushMaxRounds; ++g) {
                         if (lrow[g] != 0xFFFFFFFFu) {
-                            const unsigned pi = pre[g * 8 + warp] + rk[g];
-                            if (pi < q.cap) bulk_row_g2s(pk + (size_t)pi * D, p.x + (pas + lrow[g]) * D, ROWB, ldbar);
+                            const unsigned pi = pre[g * kPushWarps + warp] + rk[g];
+                            if (pi < q.cap) bulk_row_g2s(pk + (size_t)pi * D, p.x + (pas + lrow[g]) * D, ROWB, gbar + b);
                         }
                     }
-                    kbar_wait(ldbar, ldphase);
-                    ldphase ^= 1;
-                    PUSH_TICK(2);
-                    if (tid == 0) {
-                        if (nsend) {
-                            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                            double *dst = q.peer_recv[dest] + (((size_t)par * G + me) * q.nchunks + c) * q.cap * D;
-                            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst),
-                                         "r"((unsigned)__cvta_generic_to_shared(pk)), "r"(nsend * ROWB)
-                                         : "memory");
-                        }
-                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                        unsigned long long *fl = q.peer_flags[dest] + (size_t)me * q.nchunks + c;
-                        if (unit & 1) {
-                            pf1 = fl;
-                            pv1 = ready;
-                        } else {
-                            pf0 = fl;
-                            pv0 = ready;
-                        }
+                    if (tid == 0) {  // sent at the next service point
+                        snd->pending = 1;
+                        snd->buf = b;
+                        snd->bytes = nsend * ROWB;
+                        snd->dst = q.peer_recv[dest] + (((size_t)par * G + me) * q.nchunks + c) * q.cap * D;
+                        snd->flag = q.peer_flags[dest] + (size_t)me * q.nchunks + c;
                     }
                     ++unit;
-                    PUSH_TICK(3);
+                    PUSH_TICK(2);
 #ifdef KMC_PUSH_PROF
                     ++npush;
 #endif
                 }
             } else if (c >= q.lag) {
                 // ------------------------------------------------------------ update(c - lag)
+                PUSH_TICK(9);
                 const unsigned cu = c - q.lag;
                 const unsigned l0 = cu * q.chunk;            // first local position of the chunk
                 const unsigned lim = min(q.chunk, S - l0);
                 // pass 1: owner and packed-message row of every walker's partner
-                PUSH_TICK(9);
                 unsigned char own8[kPushMaxRounds], rk8[kPushMaxRounds];
-                // No flag of mine may stay unpublished while I wait for somebody else's (two CTAs on two GPUs could
-                // otherwise wait for each other's deferred flags): complete my stores and publish first.
-                if (tid == 0 && (pf0 || pf1)) {
-                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                    publish_pending(true, true);
-                }
-                PUSH_TICK(4);
-                cnt[tid] = 0u;  // kPushSlots * kPushMaxRanks == T (the previous task ended with a CTA barrier)
-                __syncthreads();
 #pragma unroll
                 for (int g = 0; g < kPushMaxRounds; ++g) {
                     own8[g] = 0xFF;
                     rk8[g] = 0;
+                    unsigned owner = 0xFFu;
                     if (g < (int)q.rounds) {
                         const unsigned off = g * T + tid;
-                        unsigned owner = 0xFFu;
                         if (off < lim) owner = partner_pos(p, h, me * S + l0 + off) / S;
                         own8[g] = (unsigned char)owner;
-                        for (unsigned o = 0; o < G; ++o) {
-                            const unsigned b = __ballot_sync(0xffffffffu, owner == o);
-                            if (owner == o) rk8[g] = (unsigned char)__popc(b & ((1u << lane) - 1u));
-                            if (lane == 0) cnt[(g * 8 + warp) * kPushMaxRanks + o] = __popc(b);
-                        }
+                    }
+                    for (unsigned o = 0; o < G; ++o) {
+                        const unsigned bl = __ballot_sync(0xffffffffu, owner == o);
+                        if (owner == o) rk8[g] = (unsigned char)__popc(bl & ((1u << lane) - 1u));
+                        if (lane == 0) cnt[(g * kPushWarps + warp) * kPushMaxRanks + o] = __popc(bl);
                     }
                 }
                 __syncthreads();
+                PUSH_TICK(5);
                 if (warp == 0) {
                     for (unsigned o = 0; o < G; ++o) {
                         const unsigned v = cnt[lane * kPushMaxRanks + o];
@@ -296,16 +353,25 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
                         }
                         pre[lane * kPushMaxRanks + o] = incl - v;
                     }
-                    // every source's rows of this chunk have landed in my ring (their flags were set after their stores)
-                    PUSH_TICK(5);
-                    if (lane < G && lane != me) flag_wait(q.flags + (size_t)lane * q.nchunks + cu, ready);
+                    if (lane == 0) service();
+                    // every source's rows of this chunk must have landed in my ring (flags are set after the stores).
+                    // No flag of mine may stay unpublished while I wait for somebody else's (two CTAs on two GPUs could
+                    // otherwise wait for each other's deferred flags): publish everything before blocking.
+                    const bool need = lane < G && lane != me;
+                    const unsigned long long *fl = q.flags + (size_t)(need ? lane : 0) * q.nchunks + cu;
+                    const bool late = need && flag_peek(fl) < ready;
+                    if (__any_sync(0xffffffffu, late)) {
+                        if (lane == 0) publish(true, ready);
+                        if (late) flag_wait(fl, ready);
+                    }
                     PUSH_TICK(6);
                 }
                 __syncthreads();
 #pragma unroll
                 for (int g = 0; g < kPushMaxRounds; ++g)
                     if (own8[g] != 0xFF)
-                        rowidx[g * T + tid] = (unsigned short)(pre[(g * 8 + warp) * kPushMaxRanks + own8[g]] + rk8[g]);
+                        rowidx[g * T + tid] =
+                            (unsigned short)(pre[(g * kPushWarps + warp) * kPushMaxRanks + own8[g]] + rk8[g]);
                 asm volatile("fence.proxy.async;" ::: "memory");  // acquired peer writes -> this thread's bulk gathers
 
                 // pass 2: the walker-steps, in groups of T (emcee_bulk_kernel's group loop)
@@ -314,7 +380,12 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
                     const unsigned rows = min(T, lim - g * T);
                     const unsigned l = l0 + g * T + tid;  // local position
                     const bool live = tid < rows;
-                    double *ownb = unit_begin();
+                    double *ownb = buf + (size_t)(unit & 1) * T * D;
+                    if (tid == 0) {
+                        buffer_free();
+                        publish(false, ready);
+                    }
+                    __syncthreads();  // buf[unit & 1] and xpart are free
                     if (tid == 0) {
                         kbar_expect_tx(ldbar, rows * ROWB * 2);
                         bulk_row_g2s(ownb, p.x + (act + l0 + (size_t)g * T) * D, rows * ROWB, ldbar);
@@ -380,7 +451,13 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> bulk store
                     __syncthreads();
-                    if (tid == 0) bulk_s2g(p.x + (act + l0 + (size_t)g * T) * D, ownb, rows * ROWB);
+                    if (tid == 0) {
+                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                                         p.x + (act + l0 + (size_t)g * T) * D),
+                                     "r"((unsigned)__cvta_generic_to_shared(ownb)), "r"(rows * ROWB)
+                                     : "memory");
+                        commit();
+                    }
                     ++unit;
                 }
                 PUSH_TICK(7);
@@ -401,8 +478,9 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
             if (++phase == p.nthin) phase = 0;
         }
         if (tid == 0) {  // all of this CTA's stores are complete: the last flags go out, own rows are final
+            service();
+            publish(true, ready);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            publish_pending(true, true);
             asm volatile("fence.proxy.async;" ::: "memory");
         }
         tbeg = tend;
@@ -421,9 +499,9 @@ __global__ void __launch_bounds__(kPushThreads, 3) emcee_push_kernel(const RunPa
     }
 #ifdef KMC_PUSH_PROF
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
-        printf("push rank %u cta %d: pushes %u updates %u | cycles: unit_begin %lld enum+scan %lld gather %lld send %lld | "
-               "flush %lld pass1 %lld flagwait %lld groups %lld | handoff %lld barrier+other %lld\n",
-               me, (int)blockIdx.x, npush, nupd, pt[0], pt[1], pt[2], pt[3], pt[4], pt[5], pt[6], pt[7], pt[8], pt[9]);
+        printf("push rank %u cta %d: pushes %u updates %u | cycles: sender %lld enum %lld gather-issue %lld | "
+               "pass1 %lld scan+flags %lld groups %lld | handoff %lld barrier+other %lld\n",
+               me, (int)blockIdx.x, npush, nupd, pt[0], pt[1], pt[2], pt[5], pt[6], pt[7], pt[8], pt[9]);
 #endif
 }
 

@@ -93,6 +93,14 @@ def test_int_acorr_torch_path_matches_numpy(km):
     t0, c0 = km.int_acorr(x, warn=False)
     t1, c1 = km.int_acorr(torch.from_numpy(x), warn=False)          # CPU tensor: same code path as CUDA tensors
     np.testing.assert_allclose(t1, t0, rtol=1e-9)
-    if torch.cuda.is_available():
-        t2, _ = km.int_acorr(torch.from_numpy(x).cuda(), warn=False)
-        np.testing.assert_allclose(t2, t0, rtol=1e-9)
+
+
+@pytest.mark.gpu
+def test_int_acorr_cuda_tensor_matches_numpy(km):
+    """The batched device FFT path on a CUDA tensor (the branch the CPU suite cannot reach)."""
+    import torch
+    x = np.stack([_ar1(0.5, 16, 3000, 3), _ar1(0.8, 16, 3000, 4)], axis=-1)
+    t0, c0 = km.int_acorr(x, warn=False)
+    t2, c2 = km.int_acorr(torch.from_numpy(x).cuda(), warn=False)
+    np.testing.assert_allclose(t2, t0, rtol=1e-9)
+    np.testing.assert_allclose(c2, c0, rtol=1e-9)

@@ -72,9 +72,10 @@ def test_logistic_eval_and_validation(km, orc):
     ld = km.logistic(X, y, prior_sigma=10.0)
     od = orc.Density("logistic", 32, [10.0], data=np.concatenate([X.ravel(), y]))
     pts = tstar + 0.05 * np.random.default_rng(2).standard_normal((70, 32))
-    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=0, atol=2e-3)     # default: tcgen05 path
-    ld.set_option("tensor_cores", 0)                                              # exact FP64 kernel
-    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-10)
+    assert ld.info("tensor_cores") == 0.0 and ld.info("tensor_cores_available") == 1.0
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-10)            # default: exact FP64 kernel
+    ld.set_option("tensor_cores", 1)                                              # opt-in: tcgen05 path
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=0, atol=2e-3)
     with pytest.raises(km.KmcError):
         km.LogDensity("logistic", 32, [10.0])                       # no data
     with pytest.raises(km.KmcError):
@@ -122,7 +123,8 @@ def test_logistic_tensor_core_path_matches_fp64(km):
     256-row tile (tail masking) and W is not a multiple of 128 (padded rows)."""
     N, d = 50_001, 32
     X, y, tstar = cases.logistic_problem(N=N, d=d, seed=11)
-    ld = km.logistic(X, y, prior_sigma=10.0)
+    assert km.logistic(X, y).info("tensor_cores") == 0.0           # approximate path: never on by default
+    ld = km.logistic(X, y, prior_sigma=10.0, tensor_cores=True)
     assert ld.info("tensor_cores") == 1.0 and ld.info("batched") == 2.0
     pts = tstar + 0.01 * np.random.default_rng(3).standard_normal((300, d))
     got = ld.eval(pts)
@@ -141,9 +143,14 @@ def test_logistic_tensor_core_path_matches_fp64(km):
 def test_logistic_tensor_core_not_used_when_ineligible(km):
     X, y, _ = cases.logistic_problem(N=2000, d=32, seed=1)
     X2 = X + np.float32(1e-4)                                   # not bf16-representable any more
-    assert km.logistic(X2, y).info("tensor_cores") == 0.0
     X8, y8, _ = cases.logistic_problem(N=2000, d=8, seed=1)     # d != 32
-    assert km.logistic(X8, y8).info("tensor_cores") == 0.0
+    for ld in (km.logistic(X2, y), km.logistic(X8, y8)):
+        assert ld.info("tensor_cores_available") == 0.0 and ld.info("tensor_cores") == 0.0
+        with pytest.raises(km.KmcError) as e:                   # asking for it is an error, never a silent FP64 run
+            ld.set_option("tensor_cores", 1)
+        assert e.value.code == 3
+    with pytest.raises(km.KmcError):
+        km.logistic(X8, y8, tensor_cores=True)
 
 
 def test_logistic_tensor_core_sampling(km):
@@ -152,7 +159,7 @@ def test_logistic_tensor_core_sampling(km):
     accept counts agree and the posterior moments agree within Monte Carlo error."""
     N, d, nw = 30_000, 32, 512
     X, y, tstar = cases.logistic_problem(N=N, d=d, seed=12)
-    ld = km.logistic(X, y, prior_sigma=10.0)
+    ld = km.logistic(X, y, prior_sigma=10.0, tensor_cores=True)
     x0 = tstar + cases.ball(np.zeros(d), 0.01, nw, 2)
     kw = dict(niter=120 * nw, nburnin=60 * nw, nthin=4, use_progress_meter=False, seed=3)
     th_tc, ar_tc, lp_tc, _ = km.emcee(ld, x0, **kw)
@@ -167,6 +174,27 @@ def test_logistic_tensor_core_sampling(km):
 
 
 # ---------------------------------------------------------------------------------- tcgen05 dense Gaussian (K2)
+
+def _check_tensor_gaussian_replay(od, prm, want, th, lp, x, l, na, min_same=0.98):
+    """Replay of the oracle's draws on a tensor-core Gaussian path, every assertion unconditional.
+    A walker's whole history agrees with the oracle's iff its stored chain and final state are bit-identical (states
+    are produced by the same three IEEE operations; one different decision anywhere upstream changes the bits).
+      * those walkers: accept counts equal, stored log-densities within the path's stated tolerance 1e-5 (1 + |y|^2);
+      * they must be nearly all walkers (a decision can only differ within the tolerance of a tie);
+      * EVERY walker, agreeing or not: each stored log-density is the oracle density of the stored position within
+        the tolerance, and the final log-density that of the final position -- a diverged walker is still a valid
+        chain of the same target."""
+    nw = len(na)
+    same = np.all(th.reshape(nw, -1) == want["chain_x"].reshape(nw, -1), axis=1) & np.all(x == want["x"], axis=1)
+    assert same.mean() >= min_same, same.mean()
+    assert np.array_equal(na[same], want["naccept"][same])
+    tol = lambda ref: 1e-5 * (1.0 + 2.0 * (prm[-1] - ref))
+    assert np.all(np.abs(lp[same] - want["chain_lp"][same]) <= tol(want["chain_lp"][same]))
+    ref = od.eval(th.reshape(-1, th.shape[-1])).reshape(lp.shape)
+    assert np.all(np.abs(lp - ref) <= tol(ref)), np.max(np.abs(lp - ref) / tol(ref))
+    ref = od.eval(x)
+    assert np.all(np.abs(l - ref) <= tol(ref))
+
 
 @pytest.mark.parametrize("d,npts", [(100, 1000), (128, 129), (17, 5), (64, 4096)])
 def test_gaussian_tensor_core_path_matches_fp64(km, d, npts):
@@ -213,12 +241,7 @@ def test_gaussian_tensor_core_pipeline_states_exact(km, orc):
     th, lp, ar = s.results()
     x, l, na = s.state()
     s.close()
-    same = na == want["naccept"]
-    assert same.mean() > 0.98                      # only near-tie decisions may differ
-    if same.all():
-        assert np.array_equal(th, want["chain_x"]) and np.array_equal(x, want["x"])
-        ss = 2.0 * (prm[-1] - want["chain_lp"])
-        assert np.all(np.abs(lp - want["chain_lp"]) <= 1e-5 * (1.0 + ss))
+    _check_tensor_gaussian_replay(od, prm, want, th, lp, x, l, na)
 
 
 def test_gaussian_fused_kernel_equals_three_kernel_pipeline(km):
@@ -289,8 +312,93 @@ def test_gaussian_fused_tmem_variant(km, orc):
     th, lp, ar = s.results()
     x, l, na = s.state()
     s.close()
-    same = na == want["naccept"]
-    assert same.mean() > 0.98
-    if same.all():
-        assert np.array_equal(th, want["chain_x"]) and np.array_equal(x, want["x"])
-        assert np.all(np.abs(lp - want["chain_lp"]) <= 1e-5 * (1.0 + 2.0 * (prm[-1] - want["chain_lp"])))
+    _check_tensor_gaussian_replay(od, prm, want, th, lp, x, l, na)
+
+
+# ---------------------------------------------------------------------------------- BASELINE.json sizes vs the oracle
+
+def test_gaussian100d_full_size_against_oracle(km, orc):
+    """BASELINE.json configs[2] at FULL size -- 100-D dense Gaussian, 2^16 walkers, the default fused tcgen05 kernel
+    (K2G) -- against the oracle: (a) the oracle density of a 1/997 sub-sample of every stored chain entry equals the
+    stored log-density within the stated tolerance 1e-5 (1 + |y|^2); (b) accept counts equal the number of state changes
+    in the (unthinned) chain; (c) the same sampler at 4096 walkers replays the oracle's draws (decision by decision)."""
+    d, nw, nitw = 100, 1 << 16, 8
+    prm = cases.gaussian_params(np.linspace(-1, 1, d), cases.spd_cov(d, 1))     # bench.py's configs[2] density
+    ld, od = km.LogDensity("gaussian", d, prm), orc.Density("gaussian", d, prm)
+    ld.set_option("tensor_cores", 1)
+    assert ld.info("fused_variant") == 2.0
+    x0 = 0.1 * np.random.default_rng(1000).standard_normal((nw, d))
+    s = km.Sampler(ld, x0, nitw, 0, 1, 2.0, seed=5)
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    flat_th, flat_lp = th.reshape(-1, d), lp.reshape(-1)
+    idx = np.arange(0, flat_lp.size, 997)
+    ref = od.eval(flat_th[idx])
+    tol = 1e-5 * (1.0 + 2.0 * (prm[-1] - ref))
+    assert np.all(np.abs(flat_lp[idx] - ref) <= tol), np.max(np.abs(flat_lp[idx] - ref) / tol)
+    full = np.concatenate([x0[:, None, :], th], axis=1)
+    changes = np.any(full[:, 1:] != full[:, :-1], axis=2).sum(axis=1)
+    assert np.array_equal(changes, na) and np.array_equal(ar, na / nitw)
+    assert np.array_equal(th[:, -1], x) and np.array_equal(lp[:, -1], l)
+    assert 0.01 < ar.mean() < 0.9
+    # (c) replay of the oracle at 4096 walkers, same density, same kernel
+    nw2, nit2 = 4096, 6
+    x02 = 0.1 * np.random.default_rng(7).standard_normal((nw2, d))
+    want = orc.emcee(od, x02, nit2, 1, 1, 2.0, seed=33, trace=True, nthreads=8)
+    s = km.Sampler(ld, x02, nit2, 1, 1, 2.0, 33, km.MODE_REPLAY)
+    s.set_replay(*want["trace"][:3])
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    _check_tensor_gaussian_replay(od, prm, want, th, lp, x, l, na, min_same=0.97)
+
+
+def test_logistic32d_full_size_against_oracle(km, orc):
+    """BASELINE.json configs[3] at FULL data size -- d = 32, N = 10^6, the tcgen05 kernel (K3) -- against the ORACLE's
+    FP64 density on 64 points of a realistic ensemble (ball of radius 1e-3 about theta*).  Stated tolerance: differences
+    between neighbouring points (what accept decisions see) within 2e-3; the absolute value within 0.1 (a common
+    offset of ~3e-8 per data row from the truncating FP32 accumulation, identical for every point)."""
+    N, d = 1_000_000, 32
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=1001)
+    data = np.concatenate([X.ravel(), y])
+    ld = km.logistic(X, y, prior_sigma=10.0, tensor_cores=True)
+    od = orc.Density("logistic", d, [10.0], data=data)
+    pts = tstar + 1e-3 * np.random.default_rng(5).standard_normal((64, d))
+    got, want = ld.eval(pts), od.eval(pts)
+    assert np.all(np.isfinite(got))
+    dd = (got[1:] - got[:-1]) - (want[1:] - want[:-1])
+    assert np.max(np.abs(dd)) <= 2e-3, np.max(np.abs(dd))
+    assert np.sqrt(np.mean(dd ** 2)) <= 1e-3
+    assert np.max(np.abs(got - want)) <= 0.1, np.max(np.abs(got - want))
+    off = got - want
+    assert off.max() - off.min() <= 2e-3           # the offset is common to all points
+    ld.set_option("tensor_cores", 0)               # and the exact FP64 kernel of the same plugin at this size
+    np.testing.assert_allclose(ld.eval(pts[:8]), want[:8], rtol=1e-10)
+
+
+def test_logistic_tensor_core_replay_against_oracle(km, orc):
+    """The tcgen05 logistic path in REPLAY mode against the oracle's exact run (d = 32, N = 5000, 256 walkers): walkers
+    whose whole history agrees are bit-identical in state; they are nearly all; and EVERY stored log-density is the
+    oracle density of the stored position within 2e-3."""
+    d, N, nw, nitw, nbw, nthin = 32, 5000, 256, 10, 2, 2
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=4)
+    ld = km.logistic(X, y, prior_sigma=10.0, tensor_cores=True)
+    od = orc.Density("logistic", d, [10.0], data=np.concatenate([X.ravel(), y]))
+    x0 = tstar + cases.ball(np.zeros(d), 0.05, nw, 7)
+    want = orc.emcee(od, x0, nitw, nbw, nthin, 2.0, seed=9, trace=True, nthreads=8)
+    s = km.Sampler(ld, x0, nitw, nbw, nthin, 2.0, 9, km.MODE_REPLAY)
+    s.set_replay(*want["trace"][:3])
+    s.run(-1)
+    th, lp, ar = s.results()
+    x, l, na = s.state()
+    s.close()
+    same = np.all(th.reshape(nw, -1) == want["chain_x"].reshape(nw, -1), axis=1) & np.all(x == want["x"], axis=1)
+    assert same.mean() >= 0.95, same.mean()
+    assert np.array_equal(na[same], want["naccept"][same])
+    np.testing.assert_allclose(lp[same], want["chain_lp"][same], rtol=0, atol=2e-3)
+    ref = od.eval(th.reshape(-1, d)).reshape(lp.shape)
+    np.testing.assert_allclose(lp, ref, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(l, od.eval(x), rtol=0, atol=2e-3)
