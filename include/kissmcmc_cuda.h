@@ -75,9 +75,10 @@ typedef struct kmc_emcee_opts {
      * keyed by the global walker index, so a sharded run reproduces the single-GPU run exactly. */
     int64_t shard_begin;
     int64_t shard_count;
-    /* KMC_EXCHANGE_PUSH tuning; 0 = the library's choice.  push_chunk: walkers per chunk (the unit of the "rows have
-     * landed" flags; <= 1024; default 128 * ranks), push_cap: rows per receive-ring slot (<= 256; rows past it are read
-     * from the owner directly; default 192), push_lag: chunks by which the updates trail the pushes. */
+    /* KMC_EXCHANGE_PUSH tuning; 0 = the library's choice.  push_chunk: active walkers per push (the unit of the
+     * "rows have landed" flags; <= 1024; default min(1024, 256 * ranks)), push_cap: rows per receive-ring slot (<= 384;
+     * rows past it are read from the owner directly; default mean + 8 sigma of the hit count), push_lag: chunks by
+     * which the updates trail the pushes. */
     int32_t push_chunk;
     int32_t push_cap;
     int32_t push_lag;
@@ -184,6 +185,33 @@ int32_t kmc_emcee_chain_moments(kmc_sampler_t s, double *mean, double *var, int6
 /* Current ensemble: theta [nw][d], logp [nw], naccept [nw]; any may be NULL. */
 int32_t kmc_emcee_copy_state(kmc_sampler_t s, double *theta, double *logp, int64_t *naccept);
 
+
+/* The callers either side of the sampler, on the device ------------------------------ */
+/* g-distribution helpers (src/samplers.jl:223-230).  g_pdf (:224; test-only in the reference, test/emcee.jl:2-14) and
+ * cdf_g_inv (:227) are evaluated on the host with the reference's operation order; kmc_sample_g (:230) draws n values
+ * of z on the device through the sampler's own draw path (Philox uniform -> cdf_g_inv). */
+int32_t kmc_g_pdf(const double *z, int64_t n, double a_scale, double *out);
+int32_t kmc_cdf_g_inv(const double *u, int64_t n, double a_scale, double *out);
+int32_t kmc_sample_g(double a_scale, uint64_t seed, int64_t n, int32_t device, double *out);
+/* Device-side squash_walkers (src/samplers.jl:372-428) of the sampler's stored chains: optional drop of the walkers
+ * with accept_ratio <= median - drop_fact*std (:379-393; median and std (n-1) from exact integer statistics of the
+ * accept counters), walker-major concatenation of the kept walkers (:398-399) or, with order != 0, the time-major order
+ * of the stable sortperm at :415-426.  thetas [nkept*ns][d] and logp [nkept*ns] may be NULL (then only the counts and
+ * statistics are returned: call once to size the buffers).  accept_mean = mean(accept_ratio[kept]) (:427). */
+int32_t kmc_emcee_squash(kmc_sampler_t s, int32_t drop_low_accept_ratio, double drop_fact, int32_t order,
+                         double *thetas, double *logp, int64_t *nkept, double *accept_mean, double *accept_median,
+                         double *accept_std);
+/* Device-side make_theta0s (src/samplers.jl:311-349): Gaussian ball theta0 .+ randn(d) .* ball_radius (:328-332) with
+ * counter-based Philox / Box-Muller normals, rejection of points whose plugin log-density is not > -Inf (:338), the
+ * reference's loop semantics (cumulative radius halving :326, silent skip of a walker that exhausts every try).  All
+ * pending walkers are tried at once.  out [nwalkers][d] receives the nfound (<= nwalkers) points in walker order.
+ * kmc_ball_randn returns the normals the device uses for walkers [walker0, walker0 + n), halving step k, try j
+ * (1-based like the reference loops) -- what a replay of the reference loop needs to reproduce the result. */
+int32_t kmc_make_theta0s(kmc_density_t density, const double *theta0, const double *ball_radius, int64_t nwalkers,
+                         int32_t ball_radius_halfing_steps, int32_t ntries, uint64_t seed, double *out,
+                         int64_t *nfound);
+int32_t kmc_ball_randn(uint64_t seed, int64_t walker0, int64_t nwalkers, int32_t k, int32_t j, int32_t d,
+                       int32_t device, double *out);
 
 /* Library-owned multi-GPU (single process, SURVEY.md section 8b: opts {devices[], sharded / independent}) -------- */
 /* One emcee run over `ndev` devices of this process.  devices[] lists CUDA ordinals (an ordinal may repeat: its

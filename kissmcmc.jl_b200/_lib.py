@@ -27,6 +27,7 @@ SYMBOLS = [
     "kmc_emcee_window_export", "kmc_emcee_window_attach",
     "kmc_emcee_create_multi", "kmc_multi_destroy", "kmc_multi_run", "kmc_multi_sync", "kmc_multi_last_run_ms",
     "kmc_multi_shape", "kmc_multi_copy_results",
+    "kmc_g_pdf", "kmc_cdf_g_inv", "kmc_sample_g", "kmc_emcee_squash", "kmc_make_theta0s", "kmc_ball_randn",
 ]
 
 
@@ -92,6 +93,12 @@ lib.kmc_multi_sync.argtypes = [C.c_void_p]
 lib.kmc_multi_last_run_ms.argtypes = [C.c_void_p, _dp]
 lib.kmc_multi_shape.argtypes = [C.c_void_p, _i64p, _i64p]
 lib.kmc_multi_copy_results.argtypes = [C.c_void_p, _dp, _dp, _dp]
+lib.kmc_g_pdf.argtypes = [_dp, C.c_int64, C.c_double, _dp]
+lib.kmc_cdf_g_inv.argtypes = [_dp, C.c_int64, C.c_double, _dp]
+lib.kmc_sample_g.argtypes = [C.c_double, C.c_uint64, C.c_int64, C.c_int32, _dp]
+lib.kmc_emcee_squash.argtypes = [C.c_void_p, C.c_int32, C.c_double, C.c_int32, _dp, _dp, _i64p, _dp, _dp, _dp]
+lib.kmc_make_theta0s.argtypes = [C.c_void_p, _dp, _dp, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _dp, _i64p]
+lib.kmc_ball_randn.argtypes = [C.c_uint64, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _dp]
 for _name in SYMBOLS:
     if _name not in ("kmc_version", "kmc_last_error"):
         getattr(lib, _name).restype = C.c_int32

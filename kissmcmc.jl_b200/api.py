@@ -234,6 +234,21 @@ class Sampler:
         check(lib.kmc_emcee_copy_results(self._h, _ptr(th), _ptr(lp), _ptr(ar)))
         return th, lp, ar
 
+    def squash(self, drop_low_accept_ratio=False, drop_fact=2, order=False, with_logp=True):
+        """squash_walkers (src/samplers.jl:372-428) of the stored chains ON THE DEVICE: the per-walker chains never
+        cross PCIe un-squashed.  Returns the reference 4-tuple (thetas [nkept*ns, d], mean accept ratio of the kept
+        walkers, logdensities [nkept*ns] | None, None); `self.squash_stats` holds (nkept, median, std) of the accept
+        ratios (what `verbose` prints in the reference, :386)."""
+        nk, mean, med, sd = C.c_int64(), C.c_double(), C.c_double(), C.c_double()
+        args = (int(bool(drop_low_accept_ratio)), float(drop_fact), int(bool(order)))
+        check(lib.kmc_emcee_squash(self._h, *args, None, None, C.byref(nk), C.byref(mean), C.byref(med), C.byref(sd)))
+        th = np.empty((nk.value * self.ns, self.d))
+        lp = np.empty(nk.value * self.ns) if with_logp else None
+        check(lib.kmc_emcee_squash(self._h, *args, _ptr(th), _ptr(lp), C.byref(nk), C.byref(mean), C.byref(med),
+                                   C.byref(sd)))
+        self.squash_stats = (nk.value, med.value, sd.value)
+        return th, mean.value, lp, None
+
     def chain_moments(self):
         """(mean[d], var[d], nsamples) of the whole stored chain, reduced on the device."""
         mean, var, n = np.empty(self.d), np.empty(self.d), C.c_int64()
@@ -441,9 +456,44 @@ def ball_randn(seed: int, walkers, k: int, j: int, d: int) -> np.ndarray:
     return z[:, :d]
 
 
+def ball_randn_device(seed: int, walker0: int, n: int, k: int, j: int, d: int, device: int = 0) -> np.ndarray:
+    """The standard normals the DEVICE make_theta0s uses for walkers [walker0, walker0 + n), halving step k, try j:
+    the same counter layout as ball_randn, Box-Muller evaluated with the device's log / sqrt / sincospi."""
+    out = np.empty((n, d))
+    check(lib.kmc_ball_randn(int(seed), int(walker0), int(n), int(k), int(j), int(d), int(device), _ptr(out)))
+    return out
+
+
+def g_pdf(z, a_scale: float = 2.0):
+    """src/samplers.jl:224: the density g(z) = 1/sqrt(z) / (2 (sqrt(a) - sqrt(1/a))) on [1/a, a], else 0."""
+    zz = np.ascontiguousarray(np.atleast_1d(np.asarray(z, dtype=np.float64)))
+    out = np.empty_like(zz)
+    check(lib.kmc_g_pdf(_ptr(zz), zz.size, float(a_scale), _ptr(out)))
+    return float(out[0]) if np.ndim(z) == 0 else out.reshape(np.shape(z))
+
+
+def cdf_g_inv(u, a_scale: float = 2.0):
+    """src/samplers.jl:227: (u (sqrt(a) - sqrt(1/a)) + sqrt(1/a))^2."""
+    uu = np.ascontiguousarray(np.atleast_1d(np.asarray(u, dtype=np.float64)))
+    out = np.empty_like(uu)
+    check(lib.kmc_cdf_g_inv(_ptr(uu), uu.size, float(a_scale), _ptr(out)))
+    return float(out[0]) if np.ndim(u) == 0 else out.reshape(np.shape(u))
+
+
+def sample_g(a_scale: float = 2.0, n: int | None = None, seed: int = 0, device: int = 0):
+    """src/samplers.jl:230: z ~ g, drawn on the device through the sampler's own draw path."""
+    out = np.empty(1 if n is None else int(n))
+    check(lib.kmc_sample_g(float(a_scale), int(seed), out.size, int(device), _ptr(out)))
+    return float(out[0]) if n is None else out
+
+
 def make_theta0s(theta0, ball_radius, logdensity, nwalkers, *, ball_radius_halfing_steps=7, ntries=100,
-                 hasblob=False, seed=0, randn=None):
+                 hasblob=False, seed=0, randn=None, on_device=None):
     """Initial ensemble inside a Gaussian ball around theta0, rejecting points of zero density.
+
+    With a device plugin and no `randn` callback the whole loop runs ON THE DEVICE (kmc_make_theta0s: Philox /
+    Box-Muller normals, rejection through the plugin, all pending walkers tried at once); `on_device=False` or a
+    `randn` callback selects the host loop below, which batches only the density calls.
 
     Same loop semantics as the reference, including its quirks (cumulative, never-reset radius
     halving at :326; a walker that exhausts every try is skipped, :344-345 cannot fire), but the
@@ -461,6 +511,21 @@ def make_theta0s(theta0, ball_radius, logdensity, nwalkers, *, ball_radius_halfi
     br = np.asarray(ball_radius, dtype=np.float64)
     br = np.ones(npara) * br if br.ndim == 0 else br.copy()  # :316-318
     assert br.size == npara                                  # :319
+    if on_device is None:
+        on_device = randn is None and bool(getattr(logdensity, "_h", None))
+    if on_device:
+        if randn is not None:
+            raise ValueError("a randn callback runs on the host: pass on_device=False")
+        res = np.empty((nwalkers, npara))
+        nf = C.c_int64()
+        th0c, brc = np.ascontiguousarray(th0), np.ascontiguousarray(br)
+        check(lib.kmc_make_theta0s(logdensity._h, _ptr(th0c), _ptr(brc), int(nwalkers), int(ball_radius_halfing_steps),
+                                   int(ntries), int(seed), _ptr(res), C.byref(nf)))
+        if nf.value < nwalkers:
+            warnings.warn("make_theta0s: could not find a point of non-zero density for "
+                          f"{nwalkers - nf.value} walker(s); like the reference they are silently skipped")
+        res = res[:nf.value]
+        return res[:, 0] if scalar else res
     if randn is None:
         randn = lambda w, k, j: ball_randn(seed, w, k, j, npara)
 

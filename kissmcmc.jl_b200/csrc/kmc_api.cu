@@ -164,17 +164,18 @@ bool make_map_bf16_k128(CUtensorMap *map, const void *base, unsigned long long r
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// 2-D bf16 row-major [rows][32] tensor, box = [box_rows][32], 64-byte swizzle (K-major UMMA operand)
-bool make_map_bf16_k32(CUtensorMap *map, const void *base, unsigned long long rows, unsigned box_rows) {
+// 2-D bf16 row-major [rows][kp] tensor (kp = 32 or 64), box = [box_rows][kp], swizzle = the row size in bytes
+// (64-byte / 128-byte; K-major UMMA operand)
+bool make_map_bf16_k(CUtensorMap *map, const void *base, unsigned long long rows, unsigned box_rows, int kp) {
     EncodeTiledFn fn = encode_tiled_fn();
     if (!fn) return false;
-    const cuuint64_t dims[2] = {32, rows};
-    const cuuint64_t strides[1] = {64};
-    const cuuint32_t box[2] = {32, box_rows};
+    const cuuint64_t dims[2] = {(cuuint64_t)kp, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)kp * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kp, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+              CU_TENSOR_MAP_INTERLEAVE_NONE, kp == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 constexpr int kLogitChunks = 64;
@@ -204,7 +205,7 @@ cudaError_t batch_scratch_reserve(BatchScratch &sc, const kmc_density_s &dn, lon
     const bool tcp = dn.tc_ok && dn.tc_on;
     const TcPlan pl = tcp ? tc_plan(dn, npts) : TcPlan{};
     if (tcp) {
-        const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)pl.lp.wpad * dn.d;
+        const size_t pneed = sizeof(__nv_bfloat16) * kmc::tc::PIECES * (size_t)pl.lp.wpad * dn.kp;
         if (pneed > sc.pieces_bytes) {
             dev_free(sc.pieces);
             sc.pieces = nullptr;
@@ -286,16 +287,24 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         if (e != cudaSuccess) return e;
         TcPlan pl = tc_plan(dn, npts);
         pl.lp.part = sc.part;
-        const long long ne = pl.lp.wpad * d;
-        kmc::tc::split_theta_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, sc.pieces, npts, pl.lp.wpad, d,
+        const int kp = dn.kp;  // d zero-padded to the GEMM's K (32 or 64)
+        const long long ne = pl.lp.wpad * kp;
+        kmc::tc::split_theta_kernel<<<(unsigned)((ne + 255) / 256), 256, 0, st>>>(X, sc.pieces, npts, pl.lp.wpad, d, kp,
                                                                                        1.4426950408889634);
         CUtensorMap mapA;
-        if (!make_map_bf16_k32(&mapA, sc.pieces, (unsigned long long)kmc::tc::PIECES * pl.lp.wpad, kmc::tc::BM))
+        if (!make_map_bf16_k(&mapA, sc.pieces, (unsigned long long)kmc::tc::PIECES * pl.lp.wpad, kmc::tc::BM, kp))
             return cudaErrorInvalidValue;
-        const size_t smem = sizeof(kmc::tc::Smem) + 1024;
-        e = cudaFuncSetAttribute(kmc::tc::logistic_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kmc::tc::logistic_tc_kernel<<<pl.grid, kmc::tc::kThreads, smem, st>>>(mapA, dn.mapX, pl.lp);
+        if (kp == 32) {
+            const size_t smem = sizeof(kmc::tc::Smem<32>) + 1024;
+            e = cudaFuncSetAttribute(kmc::tc::logistic_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kmc::tc::logistic_tc_kernel<32><<<pl.grid, kmc::tc::kThreads, smem, st>>>(mapA, dn.mapX, pl.lp);
+        } else {
+            const size_t smem = sizeof(kmc::tc::Smem<64>) + 1024;
+            e = cudaFuncSetAttribute(kmc::tc::logistic_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kmc::tc::logistic_tc_kernel<64><<<pl.grid, kmc::tc::kThreads, smem, st>>>(mapA, dn.mapX, pl.lp);
+        }
         const double sg = dn.params[0];
         kmc::tc::logistic_tc_finish_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(
             X, sc.part, dn.d_xty, out, npts, d, pl.lp.nchunks, 0.5 / (sg * sg));
@@ -433,8 +442,9 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
             if (e == cudaSuccess) e = cudaMemcpy(h->d_X, data, sizeof(float) * N * d, cudaMemcpyHostToDevice);
             if (e == cudaSuccess)
                 e = cudaMemcpy(h->d_y, (const float *)data + N * d, sizeof(float) * N, cudaMemcpyHostToDevice);
-            // tcgen05 path: d == 32 and every X value exactly representable in bf16
-            if (e == cudaSuccess && d == kmc::tc::BK) {
+            // tcgen05 path: d <= 64 (zero-padded to K = 32 or 64) and every X value exactly representable in bf16
+            if (e == cudaSuccess && d <= 64) {
+                h->kp = d <= 32 ? 32 : 64;
                 const uint32_t *xb = reinterpret_cast<const uint32_t *>(data);
                 bool exact = true;
                 for (long long i = 0; i < N * d && exact; ++i) exact = (xb[i] & 0xFFFFu) == 0;
@@ -450,15 +460,15 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
                         const double yc = (double)yh[n] - 0.5;
                         for (int c = 0; c < d; ++c) xty[c] += yc * (double)Xh[n * d + c];
                     }
-                    e = dev_alloc(&h->d_Xbf, sizeof(__nv_bfloat16) * N * d, device);
+                    e = dev_alloc(&h->d_Xbf, sizeof(__nv_bfloat16) * N * h->kp, device);
                     if (e == cudaSuccess) e = dev_alloc(&h->d_xty, sizeof(double) * d, device);
                     if (e == cudaSuccess) e = cudaMemcpy(h->d_xty, xty.data(), sizeof(double) * d, cudaMemcpyHostToDevice);
                     if (e == cudaSuccess) {
-                        kmc::tc::f32_to_bf16_kernel<<<(unsigned)((N * d + 255) / 256), 256>>>(h->d_X, h->d_Xbf, N * d);
+                        kmc::tc::f32_to_bf16_kernel<<<(unsigned)((N * h->kp + 255) / 256), 256>>>(h->d_X, h->d_Xbf, N, d, h->kp);
                         e = cudaDeviceSynchronize();
                     }
                     if (e == cudaSuccess)
-                        h->tc_ok = make_map_bf16_k32(&h->mapX, h->d_Xbf, (unsigned long long)N, kmc::tc::BN);
+                        h->tc_ok = make_map_bf16_k(&h->mapX, h->d_Xbf, (unsigned long long)N, kmc::tc::BN, h->kp);
                     h->tc_on = false;  // exact FP64 kernel by default; opt in with set_option("tensor_cores", 1)
                 }
             }
@@ -477,7 +487,7 @@ int32_t kmc_density_set_option(kmc_density_t h, const char *key, double value) {
     if (!strcmp(key, "tensor_cores")) {
         if (value != 0.0 && !h->tc_ok)
             return fail(KMC_ERR_UNSUPPORTED, "this density has no tcgen05 path (dense Gaussian with 16 < d <= 128; logistic "
-                                             "with d = 32 and bf16-representable data)");
+                                             "with d <= 64 and bf16-representable data)");
         h->tc_on = value != 0.0;
         return KMC_OK;
     }
@@ -633,7 +643,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         else if (density->ops.batch || !density->ops.run_push) why = "a fused (non-batched) plugin with even d";
         else if (opts->mode != KMC_MODE_PHILOX || opts->launch_mode != 0) why = "Philox draws and launch_mode 0";
         else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxChunk) why = "push_chunk in [0, 1024]";
-        else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushThreads) why = "push_cap in [0, 256]";
+        else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushMaxCap) why = "push_cap in [0, 384]";
         else if (opts->push_lag < 0) why = "push_lag >= 0";
         if (why) {
             delete s;
@@ -641,16 +651,17 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         }
         s->G = (int)(s->nhalf / s->scnt);
         s->rank = (int)(s->sbeg / s->scnt);
-        // default: a chunk sends kPushThreads/2 rows per destination on average; a ring slot holds 1.5x that
-        // (6 sigma of the binomial hit count at 8 ranks; rows past it are read from the owner directly)
+        // default: a chunk sends ~256 rows per destination (a 20 KB message), at most 1024 walkers; a ring slot holds
+        // the mean hit count + 8 sigma of its binomial spread (rows past it are read from the owner directly)
         s->chunk = opts->push_chunk > 0 ? (unsigned)opts->push_chunk
-                                        : (unsigned)std::min<long long>(kmc::kPushMaxChunk,
-                                                                        std::max<long long>(kmc::kPushThreads,
-                                                                                            (kmc::kPushThreads / 2LL) * s->G));
+                                        : (unsigned)std::min<long long>(kmc::kPushMaxChunk, 256LL * std::max(s->G, 1));
+        if (s->G == 1 && opts->push_chunk <= 0) s->chunk = kmc::kPushMaxChunk;
         s->chunk = (unsigned)std::min<long long>(s->chunk, std::max<long long>(s->scnt, 1));
         s->rounds = (s->chunk + kmc::kPushThreads - 1) / kmc::kPushThreads;
         s->nchunks = (unsigned)((s->scnt + s->chunk - 1) / s->chunk);
-        s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : (unsigned)(3 * kmc::kPushThreads / 4);
+        const double mean_hits = (double)s->chunk / s->G;
+        const unsigned want = (unsigned)(mean_hits + 8.0 * std::sqrt(mean_hits * (1.0 - 1.0 / s->G)) + 8.0);
+        s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : std::min<unsigned>(kmc::kPushMaxCap, std::max(want, 16u));
     }
     s->nstate = s->push ? 2 * s->scnt : s->nw;
     s->hoff = s->push ? s->scnt : s->nhalf;
@@ -676,7 +687,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         s->win_flags = 0;
         s->win_recv = up(sizeof(unsigned long long) * (size_t)s->G * s->nchunks);
-        s->win_x = s->win_recv + up(sizeof(double) * 2 * (size_t)s->G * s->nchunks * s->cap * d);
+        s->win_x = s->win_recv + up(2 * (size_t)s->G * s->nchunks * (kmc::kPushHeader + sizeof(double) * s->cap * d));
         s->win_bytes = s->win_x + up(sizeof(double) * (size_t)s->nstate * d);
         CU_TRY_S(cudaMalloc(&s->window, s->win_bytes));
         CU_TRY_S(cudaMemsetAsync(s->window, 0, s->win_recv, s->stream));  // flags = 0: nothing has landed
@@ -722,14 +733,15 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
     CU_TRY_S(cudaDeviceGetAttribute(&s->nsm, cudaDevAttrMultiProcessorCount, opts->device));
     if (s->push) {  // one persistent kernel, tasks handed out dynamically: as many CTAs as fit
         const void *kp = density->ops.run_push;
-        CU_TRY_S(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density->ops.push_smem));
+        const size_t psm = kmc::push_smem_bytes(d, s->cap);
+        CU_TRY_S(cudaFuncSetAttribute(kp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psm));
         int occ = 0;
-        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, kmc::kPushThreads, density->ops.push_smem));
+        CU_TRY_S(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kp, kmc::kPushThreads, psm));
         if (occ < 1) return bail(fail(KMC_ERR_CUDA, "the push kernel does not fit on the device"));
         s->grid = (unsigned)(occ * s->nsm);
         s->block = kmc::kPushThreads;
-        s->smem_bytes = density->ops.push_smem;
-        s->lag = kmc_host::push_default_lag(s->grid, s->G, s->nchunks, opts->push_lag);
+        s->smem_bytes = psm;
+        s->lag = kmc_host::push_default_lag(s->grid, s->G, s->rounds, s->nchunks, opts->push_lag);
     } else if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;

@@ -1,5 +1,9 @@
-// kmc_aux.cu -- C-ABI entry points around the sampler: library-owned multi-GPU (kmc_emcee_create_multi / kmc_multi_*).
+// kmc_aux.cu -- C-ABI entry points around the sampler: library-owned multi-GPU (kmc_emcee_create_multi / kmc_multi_*),
+// the g-distribution helpers, and the device-side squash_walkers / make_theta0s.
+#include <math_constants.h>
+
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "kmc_internal.cuh"
@@ -75,7 +79,7 @@ int32_t kmc_emcee_create_multi(const kmc_density_t *densities, const double *the
             for (int b = 0; b < ndev; ++b) share += devices[b] == devices[a] ? 1 : 0;
             sa->share = share;  // sub-samplers of one GPU must all be co-resident: split the CTA slots
             sa->grid = std::max(1u, sa->grid / (unsigned)share);
-            sa->lag = push_default_lag(sa->grid, ndev, sa->nchunks, opts->push_lag);
+            sa->lag = push_default_lag(sa->grid, ndev, sa->rounds, sa->nchunks, opts->push_lag);
             if (cudaSetDevice(devices[a]) != cudaSuccess) return bail(fail(KMC_ERR_CUDA, "cudaSetDevice(%d) failed", devices[a]));
             for (int b = 0; b < ndev; ++b) {
                 if (devices[b] != devices[a]) {
@@ -489,6 +493,256 @@ int32_t kmc_emcee_squash(kmc_sampler_t s, int32_t drop_low_accept_ratio, double 
     }
     CU_TRY_Q(cudaGetLastError());
 #undef CU_TRY_Q
+    cleanup();
+    return KMC_OK;
+}
+
+}  // extern "C"
+
+// ====================================================================================================================
+// Device-side make_theta0s (src/samplers.jl:311-349): the Gaussian ball around theta0 (:328-332), the rejection of
+// points of zero density (:338) through the log-density plugin, and the reference's loop semantics including its quirks
+// (cumulative, never-reset radius halving at :326; a walker that exhausts every try is silently skipped, :343-346).
+// The normals are counter-based: a pure function of (seed, walker, halving step k, try j, component) -- Philox4x32-10,
+// counter (walker, component pair, k<<16 | j, stream tag 0x4D54<<16), two 32-bit uniforms -> Box-Muller -- so any walker's
+// try can be (re)generated anywhere.  All walkers still pending are tried at once (normally ONE round of three kernels
+// for the whole ensemble); the host only drives the rare sequential path of a walker that needs a smaller ball.
+namespace {
+
+__device__ __forceinline__ void ball_normals(const kmc::PhiloxKeys &ks, unsigned walker, unsigned pair, unsigned kj,
+                                             double &z0, double &z1) {
+    const kmc::Philox4 r = kmc::philox4x32_10(walker, pair, kj, 0x4D540000u, ks);
+    const double u1 = ((double)r.r0 + 1.0) * 0x1p-32;  // (0, 1]
+    const double u2 = (double)r.r1 * 0x1p-32;          // [0, 1)
+    const double rad = sqrt(-2.0 * log(u1));
+    double sn, cs;
+    sincospi(2.0 * u2, &sn, &cs);
+    z0 = rad * cs;
+    z1 = rad * sn;
+}
+
+// out[i][c] = the standard normals of walker widx[i] (or w0 + i), try (k, j)
+__global__ void ball_randn_kernel(kmc::PhiloxKeys ks, const unsigned *__restrict__ widx, long long w0, long long n, int k,
+                                  int j, int d, double *__restrict__ out) {
+    const int npair = (d + 1) / 2;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * npair) return;
+    const long long i = e / npair;
+    const int pr = (int)(e - i * npair);
+    const unsigned w = widx ? widx[i] : (unsigned)(w0 + i);
+    double z0, z1;
+    ball_normals(ks, w, (unsigned)pr, ((unsigned)k << 16) | (unsigned)j, z0, z1);
+    out[i * d + 2 * pr] = z0;
+    if (2 * pr + 1 < d) out[i * d + 2 * pr + 1] = z1;
+}
+
+// candidates of the pending walkers: tmp = theta0 .+ randn(npara) .* ball_radius  (:328-332; mul, then add, no FMA)
+__global__ void ball_candidates_kernel(kmc::PhiloxKeys ks, const unsigned *__restrict__ widx, long long n, int k, int j,
+                                       int d, const double *__restrict__ th0, const double *__restrict__ br,
+                                       double *__restrict__ cand) {
+    const int npair = (d + 1) / 2;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * npair) return;
+    const long long i = e / npair;
+    const int pr = (int)(e - i * npair);
+    double z0, z1;
+    ball_normals(ks, widx[i], (unsigned)pr, ((unsigned)k << 16) | (unsigned)j, z0, z1);
+    const int c = 2 * pr;
+    cand[i * d + c] = kmc::dadd(th0[c], kmc::dmul(z0, br[c]));
+    if (c + 1 < d) cand[i * d + c + 1] = kmc::dadd(th0[c + 1], kmc::dmul(z1, br[c + 1]));
+}
+
+// :338  accepted iff logp > -Inf (NaN is not): copy the row, else the walker stays pending
+__global__ void ball_accept_kernel(const double *__restrict__ cand, const double *__restrict__ lp,
+                                   const unsigned *__restrict__ widx, long long n, int d, double *__restrict__ out,
+                                   unsigned char *__restrict__ found, unsigned *__restrict__ pend_next,
+                                   unsigned *__restrict__ npend_next) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned w = widx[i];
+    if (lp[i] > -CUDART_INF) {
+        for (int c = 0; c < d; ++c) out[(size_t)w * d + c] = cand[i * d + c];
+        found[w] = 1;
+    } else {
+        pend_next[atomicAdd(npend_next, 1u)] = w;
+    }
+}
+
+__global__ void iota_kernel(unsigned *__restrict__ a, long long n, unsigned first) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = first + (unsigned)i;
+}
+
+__global__ void min_u32_kernel(const unsigned *__restrict__ a, long long n, unsigned *__restrict__ out) {
+    unsigned m = 0xFFFFFFFFu;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = min(m, a[i]);
+    for (int o = 16; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMin(out, m);
+}
+
+__global__ void found_clear_kernel(unsigned char *__restrict__ found, long long first, long long n) {
+    const long long i = first + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) found[i] = 0;
+}
+
+// per-block counts / ordered indices of the found walkers (same two-level scan as the squash keep list)
+__global__ void __launch_bounds__(kKeepBlock) found_count_kernel(const unsigned char *__restrict__ found, long long n,
+                                                                 unsigned *__restrict__ blk_cnt) {
+    const long long w = (long long)blockIdx.x * kKeepBlock + threadIdx.x;
+    const int c = __syncthreads_count(w < n && found[w]);
+    if (threadIdx.x == 0) blk_cnt[blockIdx.x] = (unsigned)c;
+}
+__global__ void __launch_bounds__(kKeepBlock) found_gather_kernel(const unsigned char *__restrict__ found, long long n, int d,
+                                                                  const unsigned *__restrict__ blk_off,
+                                                                  const double *__restrict__ rows, double *__restrict__ out) {
+    __shared__ unsigned wc[kKeepBlock / 32];
+    const long long w = (long long)blockIdx.x * kKeepBlock + threadIdx.x;
+    const bool keep = w < n && found[w];
+    const unsigned bl = __ballot_sync(0xffffffffu, keep), lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    if (lane == 0) wc[wp] = __popc(bl);
+    __syncthreads();
+    unsigned off = blk_off[blockIdx.x];
+    for (unsigned k = 0; k < wp; ++k) off += wc[k];
+    if (keep) {
+        const size_t o = (size_t)(off + __popc(bl & ((1u << lane) - 1u))) * d;
+        for (int c = 0; c < d; ++c) out[o + c] = rows[(size_t)w * d + c];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t kmc_ball_randn(uint64_t seed, int64_t walker0, int64_t nwalkers, int32_t k, int32_t j, int32_t d, int32_t device,
+                       double *out) {
+    if (nwalkers < 0 || d < 1 || k < 1 || j < 1 || k > 0xFFFF || j > 0xFFFF || (nwalkers > 0 && !out))
+        return fail(KMC_ERR_INVALID, "bad argument");
+    if (nwalkers == 0) return KMC_OK;
+    CU_TRY(cudaSetDevice(device));
+    double *dz = nullptr;
+    CU_TRY(dev_alloc(&dz, sizeof(double) * nwalkers * d, device));
+    const long long ne = nwalkers * ((d + 1) / 2);
+    ball_randn_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(kmc::philox_keys(seed), nullptr, walker0, nwalkers, k, j, d, dz);
+    cudaError_t e = cudaMemcpy(out, dz, sizeof(double) * nwalkers * d, cudaMemcpyDeviceToHost);
+    dev_free(dz);
+    if (e != cudaSuccess) return fail(KMC_ERR_CUDA, "ball_randn failed: %s", cudaGetErrorString(e));
+    return KMC_OK;
+}
+
+int32_t kmc_make_theta0s(kmc_density_t density, const double *theta0, const double *ball_radius, int64_t nwalkers,
+                         int32_t ball_radius_halfing_steps, int32_t ntries, uint64_t seed, double *out, int64_t *nfound) {
+    if (!density || !theta0 || !ball_radius || !nfound || nwalkers < 0 || (nwalkers > 0 && !out))
+        return fail(KMC_ERR_INVALID, "bad argument");
+    if (ntries < 1 || ntries > 0xFFFF || ball_radius_halfing_steps < 1 || ball_radius_halfing_steps > 0xFFFF)
+        return fail(KMC_ERR_INVALID, "ntries and ball_radius_halfing_steps must be in [1, 65535]");
+    if (nwalkers >= (1LL << 32)) return fail(KMC_ERR_INVALID, "too many walkers");
+    *nfound = 0;
+    if (nwalkers == 0) return KMC_OK;
+    const int d = density->d, dev = density->device;
+    const long long nw = nwalkers;
+    CU_TRY(cudaSetDevice(dev));
+    const kmc::PhiloxKeys ks = kmc::philox_keys(seed);
+    std::vector<double> br(ball_radius, ball_radius + d);
+
+    double *d_th0 = nullptr, *d_br = nullptr, *d_cand = nullptr, *d_lp = nullptr, *d_rows = nullptr, *d_out = nullptr;
+    unsigned *d_pend[2] = {nullptr, nullptr}, *d_cnt = nullptr, *d_blk = nullptr;
+    unsigned char *d_found = nullptr;
+    BatchScratch sc;
+    auto cleanup = [&]() {
+        for (void *q : {(void *)d_th0, (void *)d_br, (void *)d_cand, (void *)d_lp, (void *)d_rows, (void *)d_out,
+                        (void *)d_pend[0], (void *)d_pend[1], (void *)d_cnt, (void *)d_blk, (void *)d_found, (void *)sc.part,
+                        (void *)sc.pieces})
+            dev_free(q);
+    };
+#define CU_TRY_M(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            cleanup();                                                                                   \
+            return fail(KMC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+        }                                                                                                \
+    } while (0)
+    const long long nblk = (nw + kKeepBlock - 1) / kKeepBlock;
+    CU_TRY_M(dev_alloc(&d_th0, sizeof(double) * d, dev));
+    CU_TRY_M(dev_alloc(&d_br, sizeof(double) * d, dev));
+    CU_TRY_M(dev_alloc(&d_cand, sizeof(double) * nw * d, dev));
+    CU_TRY_M(dev_alloc(&d_lp, sizeof(double) * nw, dev));
+    CU_TRY_M(dev_alloc(&d_rows, sizeof(double) * nw * d, dev));
+    CU_TRY_M(dev_alloc(&d_pend[0], sizeof(unsigned) * nw, dev));
+    CU_TRY_M(dev_alloc(&d_pend[1], sizeof(unsigned) * nw, dev));
+    CU_TRY_M(dev_alloc(&d_cnt, sizeof(unsigned) * 2, dev));
+    CU_TRY_M(dev_alloc(&d_blk, sizeof(unsigned) * 2 * nblk, dev));
+    CU_TRY_M(dev_alloc(&d_found, (size_t)nw, dev));
+    CU_TRY_M(cudaMemcpy(d_th0, theta0, sizeof(double) * d, cudaMemcpyHostToDevice));
+    CU_TRY_M(cudaMemset(d_found, 0, (size_t)nw));
+
+    // one batched try (k, j) of the walkers in d_pend[cur][0..np): candidates -> plugin -> accept / stay pending
+    auto try_round = [&](int cur, long long np, int k, int j, unsigned *np_next) -> cudaError_t {
+        cudaError_t e = cudaMemset(d_cnt, 0, sizeof(unsigned));
+        if (e != cudaSuccess) return e;
+        const long long ne = np * ((d + 1) / 2);
+        ball_candidates_kernel<<<(unsigned)((ne + 255) / 256), 256>>>(ks, d_pend[cur], np, k, j, d, d_th0, d_br, d_cand);
+        e = eval_on_device(*density, d_cand, np, d_lp, sc, nullptr);  // :334-336 through the plugin
+        if (e != cudaSuccess) return e;
+        ball_accept_kernel<<<(unsigned)((np + 255) / 256), 256>>>(d_cand, d_lp, d_pend[cur], np, d, d_rows, d_found,
+                                                                  d_pend[cur ^ 1], d_cnt);
+        return cudaMemcpy(np_next, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost);
+    };
+
+    long long i0 = 0;
+    while (i0 < nw) {  // :323 walkers i0.. with the CURRENT ball radius
+        CU_TRY_M(cudaMemcpy(d_br, br.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+        long long np = nw - i0;
+        int cur = 0;
+        iota_kernel<<<(unsigned)((np + 255) / 256), 256>>>(d_pend[0], np, (unsigned)i0);
+        for (int j = 1; j <= ntries && np > 0; ++j) {  // k = 1: radius factor 1/2^0 = 1  (:326-327)
+            unsigned nxt = 0;
+            CU_TRY_M(try_round(cur, np, 1, j, &nxt));
+            np = nxt;
+            cur ^= 1;
+        }
+        if (np == 0) break;
+        // the first walker whose k = 1 tries all failed: the reference now shrinks the ball for it AND, because the
+        // radius is never reset (:326), for every later walker -- which must therefore be redone
+        unsigned f = 0xFFFFFFFFu;
+        CU_TRY_M(cudaMemset(d_cnt + 1, 0xFF, sizeof(unsigned)));
+        min_u32_kernel<<<(unsigned)std::min<long long>((np + 255) / 256, 1184), 256>>>(d_pend[cur], np, d_cnt + 1);
+        CU_TRY_M(cudaMemcpy(&f, d_cnt + 1, sizeof(unsigned), cudaMemcpyDeviceToHost));
+        if ((long long)f + 1 < nw)
+            found_clear_kernel<<<(unsigned)((nw - f - 1 + 255) / 256), 256>>>(d_found, (long long)f + 1, nw);
+        bool got = false;
+        for (int k = 2; k <= ball_radius_halfing_steps && !got; ++k) {  // :324
+            for (int c = 0; c < d; ++c) br[c] = br[c] * (1.0 / std::pow(2.0, k - 1));  // :326 cumulative
+            CU_TRY_M(cudaMemcpy(d_br, br.data(), sizeof(double) * d, cudaMemcpyHostToDevice));
+            for (int j = 1; j <= ntries && !got; ++j) {
+                unsigned nxt = 0;
+                CU_TRY_M(cudaMemcpy(d_pend[0], &f, sizeof(unsigned), cudaMemcpyHostToDevice));
+                CU_TRY_M(try_round(0, 1, k, j, &nxt));
+                got = nxt == 0;
+            }
+        }
+        i0 = (long long)f + 1;
+    }
+
+    // :348  the found walkers, in walker order (fewer than nwalkers if some walker exhausted every try)
+    found_count_kernel<<<(unsigned)nblk, kKeepBlock>>>(d_found, nw, d_blk);
+    std::vector<unsigned> blk(2 * nblk);
+    CU_TRY_M(cudaMemcpy(blk.data(), d_blk, sizeof(unsigned) * nblk, cudaMemcpyDeviceToHost));
+    long long nf = 0;
+    for (long long b = 0; b < nblk; ++b) {
+        blk[nblk + b] = (unsigned)nf;
+        nf += blk[b];
+    }
+    if (nf > 0) {
+        CU_TRY_M(cudaMemcpy(d_blk + nblk, blk.data() + nblk, sizeof(unsigned) * nblk, cudaMemcpyHostToDevice));
+        CU_TRY_M(dev_alloc(&d_out, sizeof(double) * nf * d, dev));
+        found_gather_kernel<<<(unsigned)nblk, kKeepBlock>>>(d_found, nw, d, d_blk + nblk, d_rows, d_out);
+        CU_TRY_M(cudaMemcpy(out, d_out, sizeof(double) * nf * d, cudaMemcpyDeviceToHost));
+    }
+    CU_TRY_M(cudaGetLastError());
+#undef CU_TRY_M
+    *nfound = nf;
     cleanup();
     return KMC_OK;
 }

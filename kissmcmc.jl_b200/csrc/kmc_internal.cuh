@@ -64,6 +64,7 @@ struct kmc_density_s {
     double *d_xty = nullptr;
     CUtensorMap mapX;
     int nsm = 148;
+    int kp = 32;  // logistic on tcgen05: d zero-padded to the GEMM's K (32 or 64)
     // wide Gaussian on tcgen05: matrix A split into 3 bf16 pieces [3][128][128], TMA map
     __nv_bfloat16 *d_Abf = nullptr;
     int fused_variant = 2;       // dense Gaussian, launch_mode 0: 2 = K2G (matrix in TMEM, default), 1 = K2F (matrix in shared memory)
@@ -130,10 +131,12 @@ inline void push_set_peer(kmc_sampler_s *s, int r, unsigned char *base) {
 }
 
 // Chunks by which the updates trail the pushes.  A flag goes out about three of its CTA's tasks after its push
-// (gathers -> store -> completion -> fence + flag); a wave of the grid's tasks covers grid/G chunks, so four waves keep
-// the consumers from catching up with flags that are still on their way.
-inline unsigned push_default_lag(unsigned grid, int G, unsigned nchunks, int explicit_lag) {
-    unsigned lag = explicit_lag > 0 ? (unsigned)explicit_lag : (4u * grid + (unsigned)G - 1u) / (unsigned)G;
+// (gathers -> store -> completion -> fence + flag); a chunk index holds G-1 pushes and `rounds` update groups, so a wave
+// of the grid's tasks covers grid / (G - 1 + rounds) chunks: four waves keep the consumers from catching up with flags
+// that are still on their way.
+inline unsigned push_default_lag(unsigned grid, int G, unsigned rounds, unsigned nchunks, int explicit_lag) {
+    const unsigned per_c = (unsigned)G - 1u + rounds;
+    unsigned lag = explicit_lag > 0 ? (unsigned)explicit_lag : (4u * grid + per_c - 1u) / per_c;
     return lag < nchunks ? lag : nchunks;
 }
 

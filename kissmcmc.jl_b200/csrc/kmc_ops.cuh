@@ -12,7 +12,6 @@ struct Ops {
     const void *run_bulk[2] = {nullptr, nullptr};  // [peer] bulk (TMA) general kernel, Philox mode, even D >= 6
     size_t bulk_smem = 0;
     const void *run_push = nullptr;  // sharded ensemble with owner-computes pushes (kmc_push.cuh), Philox mode, even D
-    size_t push_smem = 0;
     size_t smem_per_walker = 0;  // bytes of shared memory per owned walker (SMEM mode)
     int block = 0;               // max threads per CTA of the run kernels
     int min_blocks = 1;          // CTAs per SM the kernels are compiled for
@@ -50,7 +49,6 @@ Ops make_ops() {
     }
     if constexpr (D % 2 == 0) {
         o.run_push = (const void *)kmc::emcee_push_kernel<Dn, D>;
-        o.push_smem = kmc::push_smem_bytes(D);
     }
     if (D <= 4) {  // shared-memory-resident variant for small rows
         o.run[0][1] = (const void *)kmc::emcee_smem_kernel<Dn, (D <= 4 ? D : 1), false>;

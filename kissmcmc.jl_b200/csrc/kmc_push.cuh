@@ -10,37 +10,43 @@
 // (SURVEY.md section 7.2(9)(i)).  Per half-step every rank runs two kinds of tasks, handed out to its CTAs from one
 // atomic counter in a fixed order:
 //
-//   push(c, dest)   enumerate the partner draws of chunk c (`chunk` consecutive active walkers) of rank `dest`; the
-//                   hits in my passive shard are gathered (one bulk copy per row), PACKED in walker order in shared
-//                   memory and sent as ONE bulk store (cp.async.bulk shared -> peer global, up to cap*8D bytes) into
-//                   dest's receive ring slot (half-step parity, source = me, chunk c); when the store has completed,
-//                   the "chunk ready" flag (source, c) in dest's memory is set to h+1 (release at system scope).
-//   update(c)       the stretch-move step of my chunk c: the same draws give every walker's owner and its rank among
-//                   the chunk's walkers with that owner = its row in the packed message; waits for the G-1 chunk
-//                   flags, then runs the bulk kernel's group loop (kmc_kernels.cuh, emcee_bulk_kernel) with the
-//                   partner row gathered from the local receive ring (remote owner), the local passive shard (own
-//                   rows) or, for the rare row past the ring slot's capacity, straight from the owner's memory.
+//   push(c, dest)   enumerate the partner draws of chunk c (`chunk` <= 1024 consecutive active walkers, `rounds` rounds
+//                   of 256) of rank `dest`; the hits in my passive shard are gathered (one bulk copy per row), PACKED
+//                   in walker order behind a 16-byte header (the message row at which each round starts) in shared
+//                   memory and sent as ONE bulk store (cp.async.bulk shared -> peer global, 16 + rows*8D bytes, 10-30 KB)
+//                   into dest's receive ring slot (half-step parity, source = me, chunk c); when the store has
+//                   completed, the "chunk ready" flag (source, c) in dest's memory is set to h+1 (release, system scope).
+//   update(c, g)    the stretch-move step of round g (256 walkers) of my chunk c: the walker-step's own draws give every
+//                   walker's owner and its rank among the round's walkers with that owner; header[g] + rank is its row
+//                   in the owner's message.  Waits for the G-1 chunk flags, then one group of the bulk kernel's loop
+//                   (kmc_kernels.cuh, emcee_bulk_kernel): own rows in one bulk load, partner rows gathered from the
+//                   local receive ring (remote owner), the local passive shard (own rows) or, for the rare row past
+//                   the ring slot's capacity, straight from the owner's memory; accept / update / chain store; own rows
+//                   back in one bulk store.
 //
-// update(c) is handed out `lag` chunks after push(c, *), so transfers are in flight while earlier chunks are updated;
-// there is no cross-GPU barrier at all -- a consumer starts as soon as ITS chunk's rows have landed -- and one local
-// grid barrier per half-step (random rows of the whole shard are read by the next half-step's pushes).
+// update(c, *) is handed out `lag` chunks after push(c, *), so transfers are in flight while earlier chunks are
+// updated; there is no cross-GPU barrier at all -- a consumer starts as soon as ITS chunk's rows have landed -- and one
+// local grid barrier per half-step (random rows of the whole shard are read by the next half-step's pushes).
 //
 // Nothing a push does is waited for where it is issued (thread 0 is the CTA's "sender"):
-//   * the row gathers of push t land while the CTA enumerates its NEXT task; the sender issues the bulk store of push t
+//   * the row gathers of push t land while the CTA works on its NEXT task; the sender issues the bulk store of push t
 //     at that task's service point (after its enumeration);
 //   * the store's completion is not waited for either: a flag is published (system-scope fence + store; kPushBatch
 //     flags per fence) at a later service point, once `cp.async.bulk.wait_group 1` says its store is complete -- or
 //     when the CTA is about to block on somebody else's flag, or at the end of the half-step.
 //
-// Why there is no deadlock: give push(c, *) level c and update(c) level c + lag + 1/2.  Tasks are taken in level order
-// by co-resident CTAs (cooperative launch), a task only ever waits for strictly lower levels of the same half-step on
-// other GPUs, pushes wait for nothing, and a CTA never blocks while it holds an unpublished flag.  Why two ring
+// Why there is no deadlock: give push(c, *) level c and update(c, *) level c + lag + 1/2.  Tasks are taken in level
+// order by co-resident CTAs (cooperative launch), a task only ever waits for strictly lower levels of the same half-step
+// on other GPUs, pushes wait for nothing, and a CTA never blocks while it holds an unpublished flag.  Why two ring
 // parities suffice: rank q can only push for half-step h+2 after it finished update h+1, which needs every rank's
 // pushes of h+1, which a rank sends only after its update h.
 //
 // Exactness: every walker-step is the same arithmetic on the same draws as the single-GPU kernels, so a sharded run is
 // bit-identical to the single-GPU run of the same ensemble (tests/test_gpu_push.py).
 #pragma once
+#ifdef KMC_PUSH_PROF
+#include <cstdio>
+#endif
 #include "kmc_kernels.cuh"
 
 namespace kmc {
@@ -61,7 +67,11 @@ constexpr int kPushFifo = 8;    // flags whose store is issued but which are not
 #ifndef KMC_PUSH_BATCH
 #define KMC_PUSH_BATCH 1
 #endif
-constexpr unsigned kPushBatch = KMC_PUSH_BATCH;  // flags published per system-scope fence (1: as soon as the store is complete)
+constexpr unsigned kPushBatch = KMC_PUSH_BATCH;  // flags published per system-scope fence
+#ifndef KMC_PUSH_AGE
+#define KMC_PUSH_AGE 3
+#endif
+constexpr unsigned kPushAge = KMC_PUSH_AGE;      // a flag is published once its store is this many commits old
 static_assert(kPushMaxRounds * kPushWarps == kPushSlots, "slots = rounds x warps = one warp's lanes");
 
 struct PushParams {
@@ -76,26 +86,29 @@ struct PushParams {
     unsigned chunk;    // walkers per chunk (<= 1024)
     unsigned rounds;   // ceil(chunk / kPushThreads)
     unsigned nchunks;  // ceil(S / chunk)
-    unsigned cap;      // rows per ring slot (<= kPushThreads)
-    unsigned lag;      // update(c) follows push(c + lag, *)
+    unsigned cap;      // rows per ring slot (<= kPushMaxCap)
+    unsigned lag;      // update(c, *) follows push(c + lag, *)
 };
+constexpr int kPushMaxCap = 384;   // rows: the message buffer is 16 + cap * 8D bytes of shared memory
+constexpr int kPushHeader = 16;    // bytes: 4 x u32, the message row at which each round of the chunk starts
 
 // The sender's state: touched by thread 0 only, kept in shared memory so that it costs the other 255 threads no registers.
 struct PushSender {
     double *dst;                     // the push whose gathers are in flight and whose store is not issued yet
     unsigned long long *flag;
-    unsigned pending, buf, bytes;
-    unsigned gphase;                 // bit b: phase of gbar[b]
+    unsigned pending, bytes;
+    unsigned gphase;                 // phase of gbar
     unsigned ncommit;                // bulk store groups committed so far
+    unsigned own_commit, msg_commit; // commit index of the last store that reads the own-row / the message buffer
     unsigned fhead, ftail;           // fifo[fhead..ftail): flags of issued stores that are not published yet
-    unsigned pad;
 };
 
-// Dynamic shared memory of the kernel for rows of D doubles.
-constexpr size_t push_smem_bytes(int D) {
-    return (size_t)3 * kPushThreads * D * 8 + sizeof(PushSender) + sizeof(unsigned long long) * (4 + kPushFifo) +
-           sizeof(unsigned) * (2 * kPushSlots * kPushMaxRanks + kPushMaxRanks + kPushFifo) +
-           sizeof(unsigned short) * kPushMaxChunk;
+// Dynamic shared memory: own rows [T][D] | partner rows [T][D] | message (header + cap rows) | sender | barriers |
+// flag queue | hit counts and prefixes.
+constexpr size_t push_smem_bytes(int D, unsigned cap) {
+    return (size_t)2 * kPushThreads * D * 8 + kPushHeader + (size_t)cap * D * 8 + sizeof(PushSender) +
+           sizeof(unsigned long long) * (4 + kPushFifo) +
+           sizeof(unsigned) * (2 * kPushSlots * kPushMaxRanks + kPushMaxRanks + kPushFifo);
 }
 
 // The partner draw alone (src/samplers.jl:250): the owner side of a push needs nothing else of the walker-step.
@@ -133,35 +146,34 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     static_assert(D % 2 == 0, "rows must be multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char push_smem[];
     constexpr unsigned T = kPushThreads, ROWB = D * 8;
-    double *buf = reinterpret_cast<double *>(push_smem);  // [2][T][D]: own rows of an update group | packed rows of a push
-    double *xpart = buf + 2 * T * D;                      // [T][D] partner rows of an update group
-    PushSender *snd = reinterpret_cast<PushSender *>(xpart + T * D);
-    unsigned long long *ldbar = reinterpret_cast<unsigned long long *>(snd + 1);        // loads of an update group
-    unsigned long long *gbar = ldbar + 1;                 // [2] row gathers of the push that owns buf[b]
+    double *ownb = reinterpret_cast<double *>(push_smem);  // [T][D] own rows of an update group
+    double *xpart = ownb + T * D;                          // [T][D] partner rows of an update group
+    unsigned char *msg = reinterpret_cast<unsigned char *>(xpart + T * D);  // header + packed rows of a push
+    PushSender *snd = reinterpret_cast<PushSender *>(msg + kPushHeader + (size_t)q.cap * ROWB);
+    unsigned long long *ldbar = reinterpret_cast<unsigned long long *>(snd + 1);  // loads of an update group
+    unsigned long long *gbar = ldbar + 1;                 // row gathers of the push that owns the message buffer
     unsigned long long *next_slot = ldbar + 3;            // broadcast of the next task id
     unsigned long long **fifo = reinterpret_cast<unsigned long long **>(ldbar + 4);  // [kPushFifo] sender's flag queue
     unsigned *cnt = reinterpret_cast<unsigned *>(ldbar + 4 + kPushFifo);  // [kPushSlots][kPushMaxRanks] hits per slot, owner
     unsigned *pre = cnt + kPushSlots * kPushMaxRanks;     // exclusive prefix of cnt over the slots, per owner
     unsigned *tot = pre + kPushSlots * kPushMaxRanks;     // [kPushMaxRanks] totals
     unsigned *fidx = tot + kPushMaxRanks;                 // [kPushFifo] commit index of the store behind fifo[k]
-    unsigned short *rowidx = reinterpret_cast<unsigned short *>(fidx + kPushFifo);  // [chunk] row in the packed message
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const unsigned S = q.S, me = q.rank, G = q.G;
-    const unsigned NT = (q.nchunks + q.lag) * G;  // tasks per half-step
+    const unsigned S = q.S, me = q.rank, G = q.G, R = q.rounds;
+    const unsigned per_c = G - 1 + R;                 // tasks per chunk index: G-1 pushes, then R update groups
+    const unsigned NT = (q.nchunks + q.lag) * per_c;  // tasks per half-step
     if (tid == 0) {
         kbar_init(ldbar, 1);
         kbar_init(gbar, 1);
-        kbar_init(gbar + 1, 1);
-        snd->pending = snd->gphase = snd->ncommit = snd->fhead = snd->ftail = 0u;
+        snd->pending = snd->gphase = snd->ncommit = snd->own_commit = snd->msg_commit = snd->fhead = snd->ftail = 0u;
     }
     __syncthreads();
-    unsigned ldphase = 0, unit = 0;
+    unsigned ldphase = 0;
 
     // ------------------------------------------------------------------ the sender (thread 0)
-    // A "unit" is a push task or an update group: it owns buf[unit & 1] and commits exactly ONE bulk store group
-    // (a push commits it one service point later).  snd_*: the push whose gathers are in flight and whose store is not
-    // issued yet.  fifo[fhead..ftail): flags of issued stores; fidx[k]: the commit index of the store behind fifo[k].
+    // snd->pending: a push whose gathers are in flight into `msg` and whose store is not issued yet.
+    // fifo[fhead..ftail): flags of issued stores; fidx[k]: the commit index of the store behind fifo[k].
     auto commit = [&]() {
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         snd->ncommit += 1;
@@ -169,16 +181,14 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     // issue the bulk store of the pending push (its gathers have landed by now: they were issued a task ago)
     auto service = [&]() {
         if (!snd->pending) return;
-        const unsigned sb = snd->buf;
-        kbar_wait(gbar + sb, (snd->gphase >> sb) & 1u);
-        snd->gphase ^= 1u << sb;
-        if (snd->bytes) {
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(snd->dst),
-                         "r"((unsigned)__cvta_generic_to_shared(buf + (size_t)sb * T * D)), "r"(snd->bytes)
-                         : "memory");
-        }
+        kbar_wait(gbar, snd->gphase & 1u);
+        snd->gphase ^= 1u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // the header (generic proxy) -> bulk store
+        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(snd->dst),
+                     "r"((unsigned)__cvta_generic_to_shared(msg)), "r"(snd->bytes)
+                     : "memory");
         commit();
+        snd->msg_commit = snd->ncommit;
         const unsigned ft = snd->ftail;
         fifo[ft % kPushFifo] = snd->flag;
         fidx[ft % kPushFifo] = snd->ncommit;
@@ -195,13 +205,15 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             upto = ftail;
         } else {
-            while (upto != ftail && fidx[upto % kPushFifo] + 1 <= ncommit) ++upto;  // complete after wait_group 1
+            // a message drains into NVLink at the link's pace: only stores at least kPushAge commits old are taken
+            // (wait_group kPushAge then returns at once, barring a congested link)
+            while (upto != ftail && fidx[upto % kPushFifo] + kPushAge <= ncommit) ++upto;
             if (upto - fhead < kPushBatch && ftail - fhead < kPushFifo - 1) return;  // batch not worth a fence yet
             if (upto == fhead) {  // queue full of young stores: wait for all of them
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 upto = ftail;
             } else {
-                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPushAge) : "memory");
             }
         }
         asm volatile("fence.proxy.async;" ::: "memory");  // the bulk stores' writes (async proxy) before the flags
@@ -210,8 +222,16 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fifo[fhead % kPushFifo]), "l"(ready) : "memory");
         snd->fhead = fhead;
     };
-    // before buf[unit & 1] is overwritten: the store that read it two units ago has finished reading
-    auto buffer_free = [&]() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); };
+    // before a shared-memory buffer is overwritten: the last bulk store that reads it has finished READING it.  Bulk
+    // groups complete in order, so it is enough that at most (groups committed after that store) are still pending --
+    // an update group must not wait for a message that is still draining into NVLink, nor a push for own-row stores.
+    auto wait_read = [&](unsigned allowed) {
+        if (allowed == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else if (allowed == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
+    };
+    auto own_free = [&]() { wait_read(snd->ncommit - snd->own_commit); };
+    auto msg_free = [&]() { wait_read(snd->ncommit - snd->msg_commit); };
 
     auto grab = [&]() -> unsigned long long { return atomicAdd(q.task_ctr, 1ULL); };  // thread 0 only
 
@@ -239,12 +259,14 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         const unsigned par = (unsigned)(h & 1);           // ring parity
         const unsigned long long ready = (unsigned long long)h + 1;
         const unsigned long long tend = tbeg + NT;
+        const size_t slot_bytes = kPushHeader + (size_t)q.cap * ROWB;  // one ring slot: header + cap rows
 
         while (next < tend) {
             const unsigned t = (unsigned)(next - tbeg);
             unsigned long long nxt = 0;
             if (tid == 0) nxt = grab();  // the atomic's round trip hides behind this task
-            const unsigned c = t / G, slot = t - c * G;
+            const unsigned c = t / per_c, slot = t - c * per_c;
+            if (tid == 0) publish(false, ready);  // flags of stores that are complete by now; behind the other warps' draws
             if (slot + 1 < G) {
                 // ------------------------------------------------------------ push(c, dest)
                 if (c < q.nchunks) {
@@ -252,15 +274,13 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                     const unsigned dest = (me + 1 + slot) % G;
                     const unsigned i0 = dest * S + c * q.chunk;  // first active walker (position in its half) of the chunk
                     const unsigned lim = min(q.chunk, S - c * q.chunk);
-                    const unsigned b = unit & 1;
-                    double *pk = buf + (size_t)b * T * D;
                     unsigned lrow[kPushMaxRounds], rk[kPushMaxRounds];
 #pragma unroll
                     for (int g = 0; g < kPushMaxRounds; ++g) {
                         lrow[g] = 0xFFFFFFFFu;
                         rk[g] = 0;
                         unsigned nh = 0;
-                        if (g < (int)q.rounds) {
+                        if (g < (int)R) {
                             const unsigned off = g * T + tid;
                             bool hit = false;
                             if (off < lim) {
@@ -286,74 +306,85 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                         }
                         pre[lane] = incl - v;
                         if (lane == 31) tot[0] = incl;
-                        if (lane == 0) {  // the sender: previous push goes out, this unit's buffer is free, flags in batches
+                        if (lane == 0) {  // the sender: the previous push goes out, then the message buffer is free again
                             service();
-                            buffer_free();
-                            publish(false, ready);
+                            msg_free();
                         }
+                        __syncwarp();
+                        if ((lane % kPushWarps) == 0)  // header: the message row at which each round starts
+                            reinterpret_cast<unsigned *>(msg)[lane / kPushWarps] = incl - v;
                     }
                     __syncthreads();
                     PUSH_TICK(0);
                     const unsigned nsend = min(tot[0], q.cap);
-                    if (tid == 0) kbar_expect_tx(gbar + b, nsend * ROWB);
+                    if (tid == 0) kbar_expect_tx(gbar, nsend * ROWB);
 #pragma unroll
                     for (int g = 0; g < kPushMaxRounds; ++g) {
                         if (lrow[g] != 0xFFFFFFFFu) {
                             const unsigned pi = pre[g * kPushWarps + warp] + rk[g];
-                            if (pi < q.cap) bulk_row_g2s(pk + (size_t)pi * D, p.x + (pas + lrow[g]) * D, ROWB, gbar + b);
+                            if (pi < q.cap)
+                                bulk_row_g2s(msg + kPushHeader + (size_t)pi * ROWB, p.x + (pas + lrow[g]) * D, ROWB, gbar);
                         }
                     }
                     if (tid == 0) {  // sent at the next service point
                         snd->pending = 1;
-                        snd->buf = b;
-                        snd->bytes = nsend * ROWB;
-                        snd->dst = q.peer_recv[dest] + (((size_t)par * G + me) * q.nchunks + c) * q.cap * D;
+                        snd->bytes = kPushHeader + nsend * ROWB;
+                        snd->dst = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(q.peer_recv[dest]) +
+                                                              (((size_t)par * G + me) * q.nchunks + c) * slot_bytes);
                         snd->flag = q.peer_flags[dest] + (size_t)me * q.nchunks + c;
                     }
-                    ++unit;
                     PUSH_TICK(2);
 #ifdef KMC_PUSH_PROF
                     ++npush;
 #endif
                 }
-            } else if (c >= q.lag) {
-                // ------------------------------------------------------------ update(c - lag)
+            } else if (c >= q.lag && (slot - (G - 1)) * T < min(q.chunk, S - (c - q.lag) * q.chunk)) {
+                // ------------------------------------------------------------ update(c - lag, g): one group of T walkers
                 PUSH_TICK(9);
-                const unsigned cu = c - q.lag;
-                const unsigned l0 = cu * q.chunk;            // first local position of the chunk
-                const unsigned lim = min(q.chunk, S - l0);
-                // pass 1: owner and packed-message row of every walker's partner
-                unsigned char own8[kPushMaxRounds], rk8[kPushMaxRounds];
-#pragma unroll
-                for (int g = 0; g < kPushMaxRounds; ++g) {
-                    own8[g] = 0xFF;
-                    rk8[g] = 0;
-                    unsigned owner = 0xFFu;
-                    if (g < (int)q.rounds) {
-                        const unsigned off = g * T + tid;
-                        if (off < lim) owner = partner_pos(p, h, me * S + l0 + off) / S;
-                        own8[g] = (unsigned char)owner;
-                    }
-                    for (unsigned o = 0; o < G; ++o) {
-                        const unsigned bl = __ballot_sync(0xffffffffu, owner == o);
-                        if (owner == o) rk8[g] = (unsigned char)__popc(bl & ((1u << lane) - 1u));
-                        if (lane == 0) cnt[(g * kPushWarps + warp) * kPushMaxRanks + o] = __popc(bl);
-                    }
+                const unsigned cu = c - q.lag, g = slot - (G - 1);
+                const unsigned l0 = cu * q.chunk + g * T;     // first local position of the group
+                const unsigned rows = min(T, min(q.chunk, S - cu * q.chunk) - g * T);
+                const unsigned l = l0 + tid;
+                const bool live = tid < rows;
+                // the walker-step's draws (:250, :252, :260 uniform); the partner's owner and the walker's rank among the
+                // round's walkers with the same owner = its row in that owner's message, after header[g]
+                DrawRec dr;
+                dr.j = 0;
+                dr.z = 0.0;
+                dr.q = 0.f;
+                unsigned owner = 0xFFu, prow = 0, rkw = 0;
+                if (live) {
+                    unsigned j;
+                    double z, u;
+                    step_draws<false>(p, h, me * S + l, j, z, u);
+                    dr.z = z;
+                    dr.q = filter_q<false>(p, z, u);
+                    const unsigned pl = j >= p.nhalf ? j - p.nhalf : j;  // position inside the passive half
+                    owner = pl / S;
+                    prow = pl - owner * S;
+                }
+                for (unsigned o = 0; o < G; ++o) {
+                    const unsigned bl = __ballot_sync(0xffffffffu, owner == o);
+                    if (owner == o) rkw = __popc(bl & ((1u << lane) - 1u));
+                    if (lane == 0) cnt[warp * kPushMaxRanks + o] = __popc(bl);
                 }
                 __syncthreads();
                 PUSH_TICK(5);
                 if (warp == 0) {
                     for (unsigned o = 0; o < G; ++o) {
-                        const unsigned v = cnt[lane * kPushMaxRanks + o];
+                        const unsigned v = lane < (unsigned)kPushWarps ? cnt[lane * kPushMaxRanks + o] : 0u;
                         unsigned incl = v;
 #pragma unroll
-                        for (int k = 1; k < 32; k <<= 1) {
+                        for (int k = 1; k < kPushWarps; k <<= 1) {
                             const unsigned u = __shfl_up_sync(0xffffffffu, incl, k);
                             if ((int)lane >= k) incl += u;
                         }
-                        pre[lane * kPushMaxRanks + o] = incl - v;
+                        if (lane < (unsigned)kPushWarps) pre[lane * kPushMaxRanks + o] = incl - v;
                     }
-                    if (lane == 0) service();
+                    if (lane == 0) {
+                        service();
+                        own_free();  // the previous group's own-row store has read its source
+                    }
                     // every source's rows of this chunk must have landed in my ring (flags are set after the stores).
                     // No flag of mine may stay unpublished while I wait for somebody else's (two CTAs on two GPUs could
                     // otherwise wait for each other's deferred flags): publish everything before blocking.
@@ -364,101 +395,74 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                         if (lane == 0) publish(true, ready);
                         if (late) flag_wait(fl, ready);
                     }
+                    __syncwarp();
                     PUSH_TICK(6);
                 }
                 __syncthreads();
-#pragma unroll
-                for (int g = 0; g < kPushMaxRounds; ++g)
-                    if (own8[g] != 0xFF)
-                        rowidx[g * T + tid] =
-                            (unsigned short)(pre[(g * kPushWarps + warp) * kPushMaxRanks + own8[g]] + rk8[g]);
                 asm volatile("fence.proxy.async;" ::: "memory");  // acquired peer writes -> this thread's bulk gathers
-
-                // pass 2: the walker-steps, in groups of T (emcee_bulk_kernel's group loop)
-                const double *ring = q.recv + (size_t)par * G * q.nchunks * q.cap * D;
-                for (unsigned g = 0; g * T < lim; ++g) {
-                    const unsigned rows = min(T, lim - g * T);
-                    const unsigned l = l0 + g * T + tid;  // local position
-                    const bool live = tid < rows;
-                    double *ownb = buf + (size_t)(unit & 1) * T * D;
-                    if (tid == 0) {
-                        buffer_free();
-                        publish(false, ready);
+                if (tid == 0) {
+                    kbar_expect_tx(ldbar, rows * ROWB * 2);
+                    bulk_row_g2s(ownb, p.x + (act + l0) * D, rows * ROWB, ldbar);
+                }
+                if (live) {
+                    const double *src;
+                    if (owner == me) {
+                        src = p.x + (pas + prow) * D;
+                    } else {
+                        const unsigned char *slotp = reinterpret_cast<const unsigned char *>(q.recv) +
+                                                     (((size_t)par * G + owner) * q.nchunks + cu) * slot_bytes;
+                        const unsigned pi = __ldcg(reinterpret_cast<const unsigned *>(slotp) + g) +
+                                            pre[warp * kPushMaxRanks + owner] + rkw;
+                        if (pi < q.cap) src = reinterpret_cast<const double *>(slotp + kPushHeader + (size_t)pi * ROWB);
+                        else src = q.peer_x[owner] + (pas + prow) * D;  // past the slot's capacity: read the owner
                     }
-                    __syncthreads();  // buf[unit & 1] and xpart are free
-                    if (tid == 0) {
-                        kbar_expect_tx(ldbar, rows * ROWB * 2);
-                        bulk_row_g2s(ownb, p.x + (act + l0 + (size_t)g * T) * D, rows * ROWB, ldbar);
-                    }
-                    DrawRec dr;
-                    dr.j = 0;
-                    dr.z = 0.0;
-                    dr.q = 0.f;
-                    if (live) {
-                        unsigned j;
-                        double z, u;
-                        step_draws<false>(p, h, me * S + l, j, z, u);  // :250, :252, (:260 uniform)
-                        dr.z = z;
-                        dr.q = filter_q<false>(p, z, u);
-                        const unsigned pl = j >= p.nhalf ? j - p.nhalf : j;  // position inside the passive half
-                        const unsigned owner = pl / S, prow = pl - owner * S;
-                        const double *src;
-                        if (owner == me) {
-                            src = p.x + (pas + prow) * D;
-                        } else {
-                            const unsigned pi = rowidx[g * T + tid];
-                            if (pi < q.cap) src = ring + (((size_t)owner * q.nchunks + cu) * q.cap + pi) * D;
-                            else src = q.peer_x[owner] + (pas + prow) * D;  // past the slot's capacity: read the owner
-                        }
-                        bulk_row_g2s(xpart + (size_t)tid * D, src, ROWB, ldbar);
-                    }
-                    const size_t k = act + l;
-                    const double lpk = live ? p.lp[k] : 0.0;
-                    kbar_wait(ldbar, ldphase);
-                    ldphase ^= 1;
-                    if (live) {
-                        double xk[D], xj[D], y[D];
+                    bulk_row_g2s(xpart + (size_t)tid * D, src, ROWB, ldbar);
+                }
+                const size_t k = act + l;
+                const double lpk = live ? p.lp[k] : 0.0;
+                kbar_wait(ldbar, ldphase);
+                ldphase ^= 1;
+                if (live) {
+                    double xk[D], xj[D], y[D];
 #pragma unroll
-                        for (int cc = 0; cc < D; cc += 2) {
-                            const double2 a2 = *reinterpret_cast<const double2 *>(ownb + (size_t)tid * D + cc);
-                            const double2 b2 = *reinterpret_cast<const double2 *>(xpart + (size_t)tid * D + cc);
-                            xk[cc] = a2.x;
-                            xk[cc + 1] = a2.y;
-                            xj[cc] = b2.x;
-                            xj[cc + 1] = b2.y;
-                        }
-                        const double z = dr.z;
-#pragma unroll
-                        for (int cc = 0; cc < D; ++cc) y[cc] = dadd(xj[cc], dmul(z, dsub(xk[cc], xj[cc])));  // :255
-                        const double p1 = dn.logpdf(y);                                                    // :257
-                        const double tt = (p1 - lpk) + (double)dr.q * 0.6931471805599453;                 // :260
-                        bool acc;
-                        if (tt > (double)p.margin) acc = true;
-                        else if (tt < -(double)p.margin) acc = false;
-                        else acc = accept_slow<false, false>(p, h, me * S + l, z, p1, lpk);
-                        if (acc) {  // :261-265
-#pragma unroll
-                            for (int cc = 0; cc < D; cc += 2)
-                                *reinterpret_cast<double2 *>(ownb + (size_t)tid * D + cc) = make_double2(y[cc], y[cc + 1]);
-                            p.lp[k] = p1;
-                            if (!reset) p.nacc[k] += 1u;
-                        }
-                        if (reset) {  // :285-288 burn-in counters are discarded (both halves of this position)
-                            p.nacc[l] = 0u;
-                            p.nacc[(size_t)S + l] = 0u;
-                        }
-                        if (store) chain_store<D>(p, chain_row(p, sidx, batch, me * S + l), acc, y, xk, p1, lpk);
+                    for (int cc = 0; cc < D; cc += 2) {
+                        const double2 a2 = *reinterpret_cast<const double2 *>(ownb + (size_t)tid * D + cc);
+                        const double2 b2 = *reinterpret_cast<const double2 *>(xpart + (size_t)tid * D + cc);
+                        xk[cc] = a2.x;
+                        xk[cc + 1] = a2.y;
+                        xj[cc] = b2.x;
+                        xj[cc + 1] = b2.y;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> bulk store
-                    __syncthreads();
-                    if (tid == 0) {
-                        asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
-                                         p.x + (act + l0 + (size_t)g * T) * D),
-                                     "r"((unsigned)__cvta_generic_to_shared(ownb)), "r"(rows * ROWB)
-                                     : "memory");
-                        commit();
+                    const double z = dr.z;
+#pragma unroll
+                    for (int cc = 0; cc < D; ++cc) y[cc] = dadd(xj[cc], dmul(z, dsub(xk[cc], xj[cc])));  // :255
+                    const double p1 = dn.logpdf(y);                                                    // :257
+                    const double tt = (p1 - lpk) + (double)dr.q * 0.6931471805599453;                 // :260
+                    bool acc;
+                    if (tt > (double)p.margin) acc = true;
+                    else if (tt < -(double)p.margin) acc = false;
+                    else acc = accept_slow<false, false>(p, h, me * S + l, z, p1, lpk);
+                    if (acc) {  // :261-265
+#pragma unroll
+                        for (int cc = 0; cc < D; cc += 2)
+                            *reinterpret_cast<double2 *>(ownb + (size_t)tid * D + cc) = make_double2(y[cc], y[cc + 1]);
+                        p.lp[k] = p1;
+                        if (!reset) p.nacc[k] += 1u;
                     }
-                    ++unit;
+                    if (reset) {  // :285-288 burn-in counters are discarded (both halves of this position)
+                        p.nacc[l] = 0u;
+                        p.nacc[(size_t)S + l] = 0u;
+                    }
+                    if (store) chain_store<D>(p, chain_row(p, sidx, batch, me * S + l), acc, y, xk, p1, lpk);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> bulk store
+                __syncthreads();
+                if (tid == 0) {
+                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.x + (act + l0) * D),
+                                 "r"((unsigned)__cvta_generic_to_shared(ownb)), "r"(rows * ROWB)
+                                 : "memory");
+                    commit();
+                    snd->own_commit = snd->ncommit;
                 }
                 PUSH_TICK(7);
 #ifdef KMC_PUSH_PROF
@@ -499,8 +503,8 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     }
 #ifdef KMC_PUSH_PROF
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
-        printf("push rank %u cta %d: pushes %u updates %u | cycles: sender %lld enum %lld gather-issue %lld | "
-               "pass1 %lld scan+flags %lld groups %lld | handoff %lld barrier+other %lld\n",
+        printf("push rank %u cta %d: pushes %u update groups %u | cycles: sender %lld enum %lld gather-issue %lld | "
+               "draws %lld scan+flags %lld group %lld | handoff %lld barrier+other %lld\n",
                me, (int)blockIdx.x, npush, nupd, pt[0], pt[1], pt[2], pt[5], pt[6], pt[7], pt[8], pt[9]);
 #endif
 }

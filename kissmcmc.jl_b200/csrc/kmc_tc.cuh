@@ -36,7 +36,7 @@
 namespace kmc {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 4, ACC = 2, PIECES = 3;
+constexpr int BM = 128, BN = 256, STAGES = 4, ACC = 2, PIECES = 3;  // K of the logistic GEMM is a template parameter: 32 or 64
 #ifndef KMC_K3_EPI
 #define KMC_K3_EPI 16
 #endif
@@ -44,10 +44,11 @@ constexpr int kEpiWarps = KMC_K3_EPI;            // 8 or 16: 2 or 4 epilogue war
 constexpr int kEpiParts = kEpiWarps / 4;         // column parts of the accumulator (a warp owns 32 rows x BN/kEpiParts columns)
 constexpr int kEpiCols = BN / kEpiParts;
 constexpr int kThreads = 32 * (2 + kEpiWarps);
-constexpr int kABytes = BM * BK * 2;  // 8 KB per theta piece
-constexpr int kBBytes = BN * BK * 2;  // 16 KB per X tile
-
+// d is zero-padded to BK = 32 (64-byte rows, SWIZZLE_64B) or, for 32 < d <= 64, to BK = 64 (128-byte rows, SWIZZLE_128B)
+template <int BK>
 struct __align__(1024) Smem {
+    static constexpr int kABytes = BM * BK * 2;  // 8 / 16 KB per theta piece
+    static constexpr int kBBytes = BN * BK * 2;  // 16 / 32 KB per X tile
     unsigned char a[PIECES][kABytes];
     unsigned char b[STAGES][kBBytes];
     unsigned long long full[STAGES], empty[STAGES], tfull[ACC], tempty[ACC], afull, aempty;
@@ -138,6 +139,21 @@ __device__ __forceinline__ unsigned long long smem_desc_sw64(unsigned addr) {
     d |= (unsigned long long)4 << 61;            // SWIZZLE_64B
     return d;
 }
+// K-major operand tile with 128-byte rows (64 bf16), SWIZZLE_128B: 8-row groups are 1024 B apart.
+__device__ __forceinline__ unsigned long long smem_desc_sw128(unsigned addr) {
+    unsigned long long d = 0;
+    d |= (unsigned long long)((addr >> 4) & 0x3FFF);
+    d |= (unsigned long long)1 << 16;
+    d |= (unsigned long long)(1024 >> 4) << 32;  // 8 rows x 128 B
+    d |= (unsigned long long)1 << 46;
+    d |= (unsigned long long)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+template <int BK>
+__device__ __forceinline__ unsigned long long smem_desc_k(unsigned addr) {
+    if constexpr (BK == 32) return smem_desc_sw64(addr);
+    else return smem_desc_sw128(addr);
+}
 // kind::f16 instruction descriptor: D = F32, A = B = BF16, both K-major, M = 128, N = 256.
 __host__ __device__ constexpr unsigned idesc_bf16_f32(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(n >> 3) << 17) | ((unsigned)(m >> 4) << 24);
@@ -201,11 +217,15 @@ struct LogitParams {
     double *part;         // [nchunks][W] partial sums of softplus
 };
 
+template <int BK>
 __global__ void __launch_bounds__(kThreads, 1)
 logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapX,
                    const LogitParams p) {
+    static_assert(BK == 32 || BK == 64, "K-major rows of 64 or 128 bytes");
     extern __shared__ unsigned char smem_raw[];
-    Smem &sm = *reinterpret_cast<Smem *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    using SmemT = Smem<BK>;
+    constexpr int kABytes = SmemT::kABytes, kBBytes = SmemT::kBBytes;
+    SmemT &sm = *reinterpret_cast<SmemT *>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
@@ -276,8 +296,8 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
                     for (int pc = PIECES - 1; pc >= 0; --pc) {  // lo, mid, hi: small terms first
                         const unsigned abase = smem_u32(sm.a[pc]);
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k)
-                            tc_mma(d, smem_desc_sw64(abase + k * 32), smem_desc_sw64(bbase + k * 32), idesc,
+                        for (int k = 0; k < BK / 16; ++k)  // 32 bytes per k-step inside the swizzled row
+                            tc_mma(d, smem_desc_k<BK>(abase + k * 32), smem_desc_k<BK>(bbase + k * 32), idesc,
                                    (pc != PIECES - 1 || k != 0) ? 1u : 0u);
                     }
                     tc_commit(&sm.empty[stage]);  // smem stage reusable once these MMAs retire
@@ -381,24 +401,30 @@ logistic_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem) : "memory");
 }
 
-// theta (FP64) -> three bf16 pieces hi + mid + lo, rows padded with zeros to wpad.
+// theta (FP64, d columns) -> three bf16 pieces hi + mid + lo, rows padded with zeros to wpad, columns to kp.
 __global__ void split_theta_kernel(const double *__restrict__ TH, __nv_bfloat16 *__restrict__ out, long long W,
-                                   long long wpad, int d, double scale) {
+                                   long long wpad, int d, int kp, double scale) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= wpad * d) return;
-    const long long w = e / d;
-    double r = w < W ? TH[e] * scale : 0.0;  // scale = log2 e: the GEMM delivers the logits in log2 units
+    if (e >= wpad * kp) return;
+    const long long w = e / kp;
+    const int c = (int)(e - w * kp);
+    double r = (w < W && c < d) ? TH[w * d + c] * scale : 0.0;  // scale = log2 e: the GEMM delivers the logits in log2 units
 #pragma unroll
     for (int pc = 0; pc < PIECES; ++pc) {
         const __nv_bfloat16 h = __double2bfloat16(r);
-        out[(size_t)pc * wpad * d + e] = h;
+        out[(size_t)pc * wpad * kp + e] = h;
         r -= (double)__bfloat162float(h);
     }
 }
 
-__global__ void f32_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long long n) {
+// X (float32 [n][d]) -> bf16 [n][kp], columns zero-padded
+__global__ void f32_to_bf16_kernel(const float *__restrict__ in, __nv_bfloat16 *__restrict__ out, long long n, int d,
+                                   int kp) {
     const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < n) out[e] = __float2bfloat16(in[e]);
+    if (e >= n * kp) return;
+    const long long r = e / kp;
+    const int c = (int)(e - r * kp);
+    out[e] = __float2bfloat16(c < d ? in[r * d + c] : 0.0f);
 }
 
 // logp = theta . (X^T (y - 1/2)) - sum_n (|s_n|/2 + log1p(e^-|s_n|)) - |theta|^2 / (2 sigma^2)
@@ -443,15 +469,6 @@ struct __align__(1024) GaussSmem {
     unsigned tmem_base;
 };
 
-__device__ __forceinline__ unsigned long long smem_desc_sw128(unsigned addr) {
-    unsigned long long d = 0;
-    d |= (unsigned long long)((addr >> 4) & 0x3FFF);
-    d |= (unsigned long long)1 << 16;
-    d |= (unsigned long long)(1024 >> 4) << 32;  // 8 rows x 128 B
-    d |= (unsigned long long)1 << 46;
-    d |= (unsigned long long)2 << 61;            // SWIZZLE_128B
-    return d;
-}
 
 struct GaussParams {
     long long W;      // points

@@ -48,7 +48,11 @@ def test_every_julia_ccall_targets_a_declared_function_with_matching_arity():
         assert ret == ("Cstring" if name == "kmc_last_error" else "Int32")
     # the stubs the reference-facing API needs are all present
     need = {"kmc_density_create", "kmc_density_eval", "kmc_emcee_create", "kmc_emcee_run", "kmc_emcee_copy_results",
-            "kmc_emcee_nsamples", "kmc_emcee_destroy", "kmc_density_destroy", "kmc_last_error"}
+            "kmc_emcee_nsamples", "kmc_emcee_destroy", "kmc_density_destroy", "kmc_last_error",
+            # round 2: plugin options, library-owned multi-GPU, the device-side rows either side of the sampler
+            "kmc_density_set_option", "kmc_density_get_info", "kmc_emcee_create_multi", "kmc_multi_run", "kmc_multi_sync",
+            "kmc_multi_shape", "kmc_multi_copy_results", "kmc_multi_destroy", "kmc_emcee_squash", "kmc_make_theta0s",
+            "kmc_g_pdf", "kmc_cdf_g_inv", "kmc_sample_g"}
     assert need <= {c[0] for c in calls}
 
 
@@ -59,7 +63,7 @@ def test_julia_pointer_and_scalar_argument_kinds_match_the_header():
         c_params = [p.strip() for p in funcs[name].split(",")] if funcs[name].strip() not in ("", "void") else []
         jl_args = [a for a in (s.strip() for s in argt.split(",")) if a]
         for cp, ja in zip(c_params, jl_args):
-            is_ptr_c = "*" in cp or cp.split()[0] in ("kmc_density_t", "kmc_sampler_t")
+            is_ptr_c = "*" in cp or cp.split()[0] in ("kmc_density_t", "kmc_sampler_t", "kmc_multi_t")
             is_ptr_j = ja.startswith(("Ptr{", "Ref{")) or ja == "Cstring"
             assert is_ptr_c == is_ptr_j, f"{name}: C parameter `{cp}` vs Julia `{ja}`"
             if not is_ptr_c:
@@ -70,3 +74,11 @@ def test_header_cites_the_reference_for_every_entry_point_group():
     """Every block of the header names the reference lines it replaces (src/samplers.jl:NNN or the :NNN shorthand)."""
     assert HEADER.count("src/samplers.jl") >= 5
     assert len(re.findall(r"[(:, ]:\d{3}", HEADER)) + HEADER.count("src/samplers.jl:") >= 15
+
+
+def test_every_header_symbol_is_bound_by_ctypes_and_exported(km):
+    """include/*.h <-> the ctypes SYMBOLS list <-> the shared library's export table (no compute calls)."""
+    funcs = header_functions()
+    assert set(funcs) == set(km.SYMBOLS), set(funcs) ^ set(km.SYMBOLS)
+    for name in funcs:
+        assert hasattr(km.lib, name), name

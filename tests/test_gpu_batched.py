@@ -143,14 +143,17 @@ def test_logistic_tensor_core_path_matches_fp64(km):
 def test_logistic_tensor_core_not_used_when_ineligible(km):
     X, y, _ = cases.logistic_problem(N=2000, d=32, seed=1)
     X2 = X + np.float32(1e-4)                                   # not bf16-representable any more
-    X8, y8, _ = cases.logistic_problem(N=2000, d=8, seed=1)     # d != 32
-    for ld in (km.logistic(X2, y), km.logistic(X8, y8)):
-        assert ld.info("tensor_cores_available") == 0.0 and ld.info("tensor_cores") == 0.0
-        with pytest.raises(km.KmcError) as e:                   # asking for it is an error, never a silent FP64 run
-            ld.set_option("tensor_cores", 1)
-        assert e.value.code == 3
+    ld = km.logistic(X2, y)
+    assert ld.info("tensor_cores_available") == 0.0 and ld.info("tensor_cores") == 0.0
+    with pytest.raises(km.KmcError) as e:                       # asking for it is an error, never a silent FP64 run
+        ld.set_option("tensor_cores", 1)
+    assert e.value.code == 3
     with pytest.raises(km.KmcError):
-        km.logistic(X8, y8, tensor_cores=True)
+        km.logistic(X2, y, tensor_cores=True)
+    X65, y65, _ = cases.logistic_problem(N=500, d=65, seed=1)   # d > 64: no kernel at all
+    with pytest.raises(km.KmcError) as e:
+        km.logistic(X65, y65)
+    assert e.value.code == 3
 
 
 def test_logistic_tensor_core_sampling(km):
@@ -171,6 +174,25 @@ def test_logistic_tensor_core_sampling(km):
     assert np.all(np.abs(t_tc.mean(0) - t64.mean(0)) < 0.5 * sd)
     assert np.all(np.abs(t_tc.std(0) - sd) < 0.3 * sd)
     assert np.all(np.abs(t_tc.mean(0) - tstar) < 6 * sd + 0.03)
+
+
+@pytest.mark.parametrize("d,N", [(16, 20_003), (48, 20_003), (64, 7_000), (5, 3_001), (33, 4_096)])
+def test_logistic_tensor_core_any_d_up_to_64(km, orc, d, N):
+    """d is zero-padded to the GEMM's K: 32 (64-byte rows, SWIZZLE_64B) for d <= 32, 64 (128-byte rows, SWIZZLE_128B)
+    for 32 < d <= 64.  Against the ORACLE density, stated tolerance 2e-3 on the value and on differences."""
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=20 + d)
+    ld = km.logistic(X, y, prior_sigma=10.0, tensor_cores=True)
+    assert ld.info("tensor_cores") == 1.0
+    od = orc.Density("logistic", d, [10.0], data=np.concatenate([X.ravel(), y]))
+    pts = tstar + 0.02 * np.random.default_rng(d).standard_normal((200, d))
+    got, want = ld.eval(pts), od.eval(pts)
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-3)
+    np.testing.assert_allclose(got[1:] - got[:-1], want[1:] - want[:-1], rtol=0, atol=2e-3)
+    # and a short sampling run on the tensor path stays a valid chain of the same target
+    nw = 2 * (d + 3)
+    x0 = tstar + cases.ball(np.zeros(d), 0.02, nw, 1)
+    th, ar, lp, _ = km.emcee(ld, x0, niter=12 * nw, nburnin=4 * nw, use_progress_meter=False, seed=2)
+    np.testing.assert_allclose(lp, od.eval(th.reshape(-1, d)).reshape(lp.shape), rtol=0, atol=2e-3)
 
 
 # ---------------------------------------------------------------------------------- tcgen05 dense Gaussian (K2)
