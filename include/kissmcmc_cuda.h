@@ -78,7 +78,8 @@ typedef struct kmc_emcee_opts {
     /* KMC_EXCHANGE_PUSH tuning; 0 = the library's choice.  push_chunk: active walkers per push (the unit of the
      * "rows have landed" flags; <= 1024; default min(1024, 256 * ranks)), push_cap: rows per receive-ring slot (<= 384;
      * rows past it are read from the owner directly; default mean + 8 sigma of the hit count), push_lag: chunks by
-     * which the updates trail the pushes. */
+     * which the updates trail the pushes in the ordered task hand-out (default 5/16 of the chunks); -1 selects the
+     * adaptive hand-out (an update is taken when its rows are seen landed, else a push). */
     int32_t push_chunk;
     int32_t push_cap;
     int32_t push_lag;

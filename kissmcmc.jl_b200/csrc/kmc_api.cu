@@ -568,6 +568,7 @@ int32_t kmc_emcee_destroy(kmc_sampler_t s) {
     if (s->push) cudaFree(s->window);  // own allocation (exported through CUDA IPC); x lives inside it
     else dev_free(s->x);
     dev_free(s->task_ctr);
+    dev_free(s->notes);
     dev_free(s->lp);
     dev_free(s->chain_x);
     dev_free(s->chain_lp);
@@ -644,7 +645,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         else if (opts->mode != KMC_MODE_PHILOX || opts->launch_mode != 0) why = "Philox draws and launch_mode 0";
         else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxChunk) why = "push_chunk in [0, 1024]";
         else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushMaxCap) why = "push_cap in [0, 384]";
-        else if (opts->push_lag < 0) why = "push_lag >= 0";
+        else if (opts->push_lag < -1) why = "push_lag >= -1";
         if (why) {
             delete s;
             return fail(KMC_ERR_UNSUPPORTED, "the push exchange needs %s", why);
@@ -693,7 +694,12 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         CU_TRY_S(cudaMemsetAsync(s->window, 0, s->win_recv, s->stream));  // flags = 0: nothing has landed
         s->x = reinterpret_cast<double *>(s->window + s->win_x);
         push_set_peer(s, s->rank, s->window);
-        CU_TRY_S(dev_alloc(&s->task_ctr, sizeof(unsigned long long), opts->device));
+        CU_TRY_S(dev_alloc(&s->task_ctr, 4 * sizeof(unsigned long long), opts->device));
+        if (s->G > 1) {  // the publisher's inbox: one note per push task, epochs only grow
+            const size_t nb = sizeof(unsigned) * (size_t)s->nchunks * (s->G - 1);
+            CU_TRY_S(dev_alloc(&s->notes, nb, opts->device));
+            CU_TRY_S(cudaMemsetAsync(s->notes, 0, nb, s->stream));
+        }
     } else {
         CU_TRY_S(dev_alloc(&s->x, sizeof(double) * s->nw * d, opts->device));
     }
@@ -741,7 +747,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         s->grid = (unsigned)(occ * s->nsm);
         s->block = kmc::kPushThreads;
         s->smem_bytes = psm;
-        s->lag = kmc_host::push_default_lag(s->grid, s->G, s->rounds, s->nchunks, opts->push_lag);
+        s->lag = kmc_host::push_default_lag(s->nchunks, opts->push_lag);
     } else if (!density->ops.batch) {   // persistent launch geometry: every CTA owns per_cta walker positions of each half and
         // every thread the same number of them (block size = per_cta / rounds, warp-rounded)
         const int r = opts->mode == KMC_MODE_REPLAY ? 1 : 0;
@@ -939,6 +945,7 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
             q.peer_x[r] = s->peer_x[r];
         }
         q.task_ctr = s->task_ctr;
+        q.notes = s->notes;
         q.S = (unsigned)s->scnt;
         q.G = (unsigned)s->G;
         q.rank = (unsigned)s->rank;
@@ -947,8 +954,12 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
         q.nchunks = s->nchunks;
         q.cap = s->cap;
         q.lag = s->lag;
+        q.batch = 1;
+        q.age = 1;
+        if (const char *e = getenv("KMC_PUSH_BATCH")) q.batch = (unsigned)std::max(1, std::min(6, atoi(e)));  // profiling knobs
+        if (const char *e = getenv("KMC_PUSH_AGE")) q.age = (unsigned)std::max(1, std::min(3, atoi(e)));
         set_range(hbeg, hend);
-        CU_TRY(cudaMemsetAsync(s->task_ctr, 0, sizeof(unsigned long long), s->stream));
+        CU_TRY(cudaMemsetAsync(s->task_ctr, 0, 4 * sizeof(unsigned long long), s->stream));
         CU_TRY(cudaEventRecord(s->ev0, s->stream));
         void *pargs[] = {&p, &q, s->dn->params.data()};
         CU_TRY(cudaLaunchCooperativeKernel(s->dn->ops.run_push, dim3(s->grid), dim3(s->block), pargs, s->smem_bytes,

@@ -79,7 +79,7 @@ int32_t kmc_emcee_create_multi(const kmc_density_t *densities, const double *the
             for (int b = 0; b < ndev; ++b) share += devices[b] == devices[a] ? 1 : 0;
             sa->share = share;  // sub-samplers of one GPU must all be co-resident: split the CTA slots
             sa->grid = std::max(1u, sa->grid / (unsigned)share);
-            sa->lag = push_default_lag(sa->grid, ndev, sa->rounds, sa->nchunks, opts->push_lag);
+            sa->lag = push_default_lag(sa->nchunks, opts->push_lag);
             if (cudaSetDevice(devices[a]) != cudaSuccess) return bail(fail(KMC_ERR_CUDA, "cudaSetDevice(%d) failed", devices[a]));
             for (int b = 0; b < ndev; ++b) {
                 if (devices[b] != devices[a]) {

@@ -114,6 +114,7 @@ struct kmc_sampler_s {
     unsigned char *window = nullptr;
     size_t win_flags = 0, win_recv = 0, win_x = 0, win_bytes = 0;  // byte offsets inside the window (same on every rank)
     unsigned long long *task_ctr = nullptr;
+    unsigned *notes = nullptr;  // push exchange: the publisher CTA's inbox (one note per push task)
     int G = 1;
     unsigned chunk = 0, rounds = 0, nchunks = 0, cap = 0, lag = 0;
     double *peer_recv[8] = {};
@@ -130,13 +131,15 @@ inline void push_set_peer(kmc_sampler_s *s, int r, unsigned char *base) {
     s->peer_x[r] = reinterpret_cast<const double *>(base + s->win_x);
 }
 
-// Chunks by which the updates trail the pushes.  A flag goes out about three of its CTA's tasks after its push
-// (gathers -> store -> completion -> fence + flag); a chunk index holds G-1 pushes and `rounds` update groups, so a wave
-// of the grid's tasks covers grid / (G - 1 + rounds) chunks: four waves keep the consumers from catching up with flags
-// that are still on their way.
-inline unsigned push_default_lag(unsigned grid, int G, unsigned rounds, unsigned nchunks, int explicit_lag) {
-    const unsigned per_c = (unsigned)G - 1u + rounds;
-    unsigned lag = explicit_lag > 0 ? (unsigned)explicit_lag : (4u * grid + per_c - 1u) / per_c;
+// Task hand-out of the push kernel.  push_lag > 0: ORDERED, update(c, *) follows push(c + lag, *); push_lag = 0: ordered
+// with the library's lag = 5/16 of the chunks (measured on 2 / 4 / 8 B200s with the 2^24-walker 10-D ensemble: the best
+// lags were 2048 of 8192, 512 of 2048 and 384 of 1024 chunks -- a flag reaches the consumer ~25 us after its push, and
+// everything before and after the overlap window is still useful work: pushes first, updates last); push_lag = -1:
+// ADAPTIVE (two counters, an update is taken when its flags are seen set, else a push; returned as lag 0).
+inline unsigned push_default_lag(unsigned nchunks, int push_lag) {
+    if (push_lag < 0) return 0u;
+    unsigned lag = push_lag > 0 ? (unsigned)push_lag : (5u * nchunks + 15u) / 16u;
+    if (lag < 1u) lag = 1u;
     return lag < nchunks ? lag : nchunks;
 }
 

@@ -7,8 +7,8 @@
 //
 // The draws are counter-based (Philox keyed by the global walker index, kmc_device.cuh), so the OWNER of a passive
 // shard can enumerate, without any index round trip, which of its rows every other rank's active walkers will ask for
-// (SURVEY.md section 7.2(9)(i)).  Per half-step every rank runs two kinds of tasks, handed out to its CTAs from one
-// atomic counter in a fixed order:
+// (SURVEY.md section 7.2(9)(i)).  Per half-step every rank runs two kinds of tasks, handed out to its CTAs from two
+// atomic counters (pushes in chunk order, update groups in chunk order):
 //
 //   push(c, dest)   enumerate the partner draws of chunk c (`chunk` <= 1024 consecutive active walkers, `rounds` rounds
 //                   of 256) of rank `dest`; the hits in my passive shard are gathered (one bulk copy per row), PACKED
@@ -24,20 +24,31 @@
 //                   the ring slot's capacity, straight from the owner's memory; accept / update / chain store; own rows
 //                   back in one bulk store.
 //
-// update(c, *) is handed out `lag` chunks after push(c, *), so transfers are in flight while earlier chunks are
-// updated; there is no cross-GPU barrier at all -- a consumer starts as soon as ITS chunk's rows have landed -- and one
-// local grid barrier per half-step (random rows of the whole shard are read by the next half-step's pushes).
+// Two hand-outs (PushParams::lag): ORDERED (the default) -- one counter, the pushes of chunk c, then the update groups
+// of chunk c - lag; the next task id is ONE atomic issued at the start of the current task, so handing out costs nothing;
+// a flag reaches its consumer ~25 us after its push, `lag` chunks of other work cover that.  ADAPTIVE (lag = 0) -- two
+// counters; a CTA takes the next update group if that group's flags are seen set, else the next push, and only when no
+// push is left an update it has to wait for (no tuning, but three dependent L2 round trips per task: measured 7 % slower
+// at 8 GPUs).  There is no cross-GPU barrier at all -- a consumer starts as soon as ITS chunk's rows have landed -- and one local
+// grid barrier per half-step (random rows of the whole shard are read by the next half-step's pushes).
 //
 // Nothing a push does is waited for where it is issued (thread 0 is the CTA's "sender"):
 //   * the row gathers of push t land while the CTA works on its NEXT task; the sender issues the bulk store of push t
 //     at that task's service point (after its enumeration);
-//   * the store's completion is not waited for either: a flag is published (system-scope fence + store; kPushBatch
-//     flags per fence) at a later service point, once `cp.async.bulk.wait_group 1` says its store is complete -- or
-//     when the CTA is about to block on somebody else's flag, or at the end of the half-step.
+//   * the store's completion is not waited for either: at a later task, once `cp.async.bulk.wait_group kPushAge` says
+//     the store is complete, the sender posts a NOTE (release at GPU scope) in local memory;
+//   * the system-scope release that the remote flag needs is not paid by the workers at all: with tens of megabytes
+//     queued on the link a `fence.acq_rel.sys` takes ~8 us (measured: a quarter of the kernel when every CTA fenced for
+//     its own flags).  ONE CTA per GPU, the publisher, takes no tasks: it sweeps the notes (acquire, GPU scope), and per
+//     sweep pays one system-scope fence for all the flags it then sets in the peers' memory.  The chain worker's stores
+//     -> release.gpu note -> publisher's acquire.gpu -> fence.sys -> flag -> consumer's acquire.sys orders the rows
+//     before the consumer's reads.
 //
-// Why there is no deadlock: give push(c, *) level c and update(c, *) level c + lag + 1/2.  Tasks are taken in level
-// order by co-resident CTAs (cooperative launch), a task only ever waits for strictly lower levels of the same half-step
-// on other GPUs, pushes wait for nothing, and a CTA never blocks while it holds an unpublished flag.  Why two ring
+// Why there is no deadlock: pushes wait for nothing (only for the link to drain their previous message); all CTAs are
+// co-resident (cooperative launch); a CTA never blocks while it holds an un-noted completed store; ORDERED: give
+// push(c, *) level c and update(c, *) level c + lag + 1/2 -- tasks are taken in level order and a task only ever waits
+// for strictly lower levels on other GPUs; ADAPTIVE: a CTA blocks on a flag only when its rank has no push left to hand
+// out, so every rank's pushes complete whatever its updates do.  Why two ring
 // parities suffice: rank q can only push for half-step h+2 after it finished update h+1, which needs every rank's
 // pushes of h+1, which a rank sends only after its update h.
 //
@@ -80,14 +91,17 @@ struct PushParams {
     double *peer_recv[kPushMaxRanks];
     unsigned long long *peer_flags[kPushMaxRanks];
     const double *peer_x[kPushMaxRanks];  // x[2][S][D] of every rank (capacity-overflow fallback reads)
-    unsigned long long *task_ctr;          // task counter (zeroed by the host before every launch)
+    unsigned long long *task_ctr;          // [2 half-step parities][push, update] task counters (zeroed by the host)
+    unsigned *notes;                       // [nchunks * (G-1)] per push task: epoch of its completed store (publisher's inbox)
     unsigned S;        // shard size: positions of each half per rank
     unsigned G, rank;  // ranks, my rank
     unsigned chunk;    // walkers per chunk (<= 1024)
     unsigned rounds;   // ceil(chunk / kPushThreads)
     unsigned nchunks;  // ceil(S / chunk)
     unsigned cap;      // rows per ring slot (<= kPushMaxCap)
-    unsigned lag;      // update(c, *) follows push(c + lag, *)
+    unsigned lag;      // > 0: ORDERED hand-out from one counter, update(c, *) follows push(c + lag, *); 0: ADAPTIVE
+    unsigned batch;    // notes posted per GPU-scope fence (>= 1)
+    unsigned age;      // a store is taken for complete once it is this many commits old (1..3)
 };
 constexpr int kPushMaxCap = 384;   // rows: the message buffer is 16 + cap * 8D bytes of shared memory
 constexpr int kPushHeader = 16;    // bytes: 4 x u32, the message row at which each round of the chunk starts
@@ -95,7 +109,7 @@ constexpr int kPushHeader = 16;    // bytes: 4 x u32, the message row at which e
 // The sender's state: touched by thread 0 only, kept in shared memory so that it costs the other 255 threads no registers.
 struct PushSender {
     double *dst;                     // the push whose gathers are in flight and whose store is not issued yet
-    unsigned long long *flag;
+    unsigned task;                   // its push task id (names the note and the flag)
     unsigned pending, bytes;
     unsigned gphase;                 // phase of gbar
     unsigned ncommit;                // bulk store groups committed so far
@@ -129,6 +143,13 @@ __device__ __forceinline__ unsigned long long flag_peek(const unsigned long long
     return cur;
 }
 
+// no ordering: only to CHOOSE a task (the update itself re-checks with acquire semantics before it reads the ring)
+__device__ __forceinline__ unsigned long long flag_peek_relaxed(const unsigned long long *flag) {
+    unsigned long long cur;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+    return cur;
+}
+
 __device__ __forceinline__ void flag_wait(const unsigned long long *flag, unsigned long long v) {
     long long t0 = 0;
     unsigned spins = 0;
@@ -153,7 +174,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     unsigned long long *ldbar = reinterpret_cast<unsigned long long *>(snd + 1);  // loads of an update group
     unsigned long long *gbar = ldbar + 1;                 // row gathers of the push that owns the message buffer
     unsigned long long *next_slot = ldbar + 3;            // broadcast of the next task id
-    unsigned long long **fifo = reinterpret_cast<unsigned long long **>(ldbar + 4);  // [kPushFifo] sender's flag queue
+    unsigned long long *fifo = ldbar + 4;                 // [kPushFifo] sender's queue: push task ids of issued stores
     unsigned *cnt = reinterpret_cast<unsigned *>(ldbar + 4 + kPushFifo);  // [kPushSlots][kPushMaxRanks] hits per slot, owner
     unsigned *pre = cnt + kPushSlots * kPushMaxRanks;     // exclusive prefix of cnt over the slots, per owner
     unsigned *tot = pre + kPushSlots * kPushMaxRanks;     // [kPushMaxRanks] totals
@@ -161,8 +182,13 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned S = q.S, me = q.rank, G = q.G, R = q.rounds;
-    const unsigned per_c = G - 1 + R;                 // tasks per chunk index: G-1 pushes, then R update groups
-    const unsigned NT = (q.nchunks + q.lag) * per_c;  // tasks per half-step
+    const unsigned NP = q.nchunks * (G - 1);  // push tasks per half-step: (chunk, destination)
+    const unsigned NU = q.nchunks * R;        // update tasks per half-step: (chunk, round of T walkers)
+    const bool ordered = q.lag > 0;           // one counter, fixed order: pushes of chunk c, then the update groups of chunk c - lag
+    const unsigned per_c = G - 1 + R;
+    const unsigned NT = (q.nchunks + q.lag) * per_c;
+    const bool use_pub = G > 1 && gridDim.x > 1;                   // the last CTA publishes flags and takes no tasks
+    const bool is_pub = use_pub && blockIdx.x == gridDim.x - 1;
     if (tid == 0) {
         kbar_init(ldbar, 1);
         kbar_init(gbar, 1);
@@ -190,7 +216,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         commit();
         snd->msg_commit = snd->ncommit;
         const unsigned ft = snd->ftail;
-        fifo[ft % kPushFifo] = snd->flag;
+        fifo[ft % kPushFifo] = snd->task;
         fidx[ft % kPushFifo] = snd->ncommit;
         snd->ftail = ft + 1;
         snd->pending = 0;
@@ -207,19 +233,37 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         } else {
             // a message drains into NVLink at the link's pace: only stores at least kPushAge commits old are taken
             // (wait_group kPushAge then returns at once, barring a congested link)
-            while (upto != ftail && fidx[upto % kPushFifo] + kPushAge <= ncommit) ++upto;
-            if (upto - fhead < kPushBatch && ftail - fhead < kPushFifo - 1) return;  // batch not worth a fence yet
+            while (upto != ftail && fidx[upto % kPushFifo] + q.age <= ncommit) ++upto;
+            if (upto - fhead < q.batch && ftail - fhead < kPushFifo - 1) return;  // batch not worth a fence yet
             if (upto == fhead) {  // queue full of young stores: wait for all of them
                 asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
                 upto = ftail;
+            } else if (q.age >= 3) {
+                asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
+            } else if (q.age == 2) {
+                asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
             } else {
-                asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPushAge) : "memory");
+                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
             }
         }
-        asm volatile("fence.proxy.async;" ::: "memory");  // the bulk stores' writes (async proxy) before the flags
-        asm volatile("fence.acq_rel.sys;" ::: "memory");
-        for (; fhead != upto; ++fhead)
-            asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fifo[fhead % kPushFifo]), "l"(ready) : "memory");
+        // wait_group made the completed stores' writes visible to this thread (completion of a bulk async-group implies
+        // the generic-async proxy fence); the release fence then orders them before the flags for every observer.  No
+        // fence.proxy.async here: it would also wait for the YOUNGER message that is still draining into the link
+        // (measured: ~20k cycles per publish, a quarter of the kernel).
+        if (use_pub) {  // hand the completed stores to the publisher CTA: release at GPU scope is all a worker pays
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            for (; fhead != upto; ++fhead)
+                asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q.notes + (unsigned)fifo[fhead % kPushFifo]),
+                             "r"((unsigned)ready)
+                             : "memory");
+        } else {  // a one-CTA grid has no publisher: set the remote flags directly
+            asm volatile("fence.acq_rel.sys;" ::: "memory");
+            for (; fhead != upto; ++fhead) {
+                const unsigned tp = (unsigned)fifo[fhead % kPushFifo], pcn = tp / (G - 1);
+                unsigned long long *fl = q.peer_flags[(me + 1 + (tp - pcn * (G - 1))) % G] + (size_t)me * q.nchunks + pcn;
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ready) : "memory");
+            }
+        }
         snd->fhead = fhead;
     };
     // before a shared-memory buffer is overwritten: the last bulk store that reads it has finished READING it.  Bulk
@@ -233,7 +277,71 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     auto own_free = [&]() { wait_read(snd->ncommit - snd->own_commit); };
     auto msg_free = [&]() { wait_read(snd->ncommit - snd->msg_commit); };
 
-    auto grab = [&]() -> unsigned long long { return atomicAdd(q.task_ctr, 1ULL); };  // thread 0 only
+    // The next task of this CTA, chosen by warp 0 (all 32 lanes call it; the result is valid in lane 0):
+    // kind << 32 | id, kind 0 = push, 1 = update, 2 = nothing left.  An update group whose chunk's flags are all set
+    // is preferred (lanes peek the G-1 flags in parallel); else a push; else an update that will have to wait.
+    auto pick = [&](unsigned par, unsigned long long ready) -> unsigned long long {
+        unsigned long long *pc = q.task_ctr + 2 * par, *uc = pc + 1;
+        // lane 30 reads the push counter, lane 31 the update counter (one round trip for both)
+        unsigned long long cv = 0;
+        if (lane >= 30) cv = *reinterpret_cast<volatile unsigned long long *>(lane == 31 ? uc : pc);
+        const unsigned long long up = __shfl_sync(0xffffffffu, cv, 31), pp = __shfl_sync(0xffffffffu, cv, 30);
+        bool late = false;
+        if (up < NU && lane < G && lane != me)
+            late = flag_peek_relaxed(q.flags + (size_t)lane * q.nchunks + (unsigned)up / R) < ready;
+        const bool ok = up < NU && !__any_sync(0xffffffffu, late);
+        unsigned long long res = 2ULL << 32;
+        if (lane == 0) {
+            bool done = false;
+            if (ok) {  // claim exactly the group whose flags were seen set (compare-and-swap: a later group might not be ready,
+                       // and a CTA must never block on a flag while its rank still has pushes to hand out)
+                if (atomicCAS(uc, up, up + 1ULL) == up) {
+                    res = (1ULL << 32) | up;
+                    done = true;
+                }
+            }
+            if (!done && pp < NP) {
+                const unsigned long long t = atomicAdd(pc, 1ULL);
+                if (t < NP) {
+                    res = t;
+                    done = true;
+                }
+            }
+            if (!done) {
+                const unsigned long long t = atomicAdd(uc, 1ULL);
+                if (t < NU) res = (1ULL << 32) | t;
+            }
+        }
+        return res;
+    };
+
+    // ORDERED hand-out: sequence number t -> chunk index c = t / (G-1+R); its first G-1 slots are the pushes of chunk c,
+    // the next R the update groups of chunk c - lag.  Slots that fall outside (c >= nchunks, c < lag, a round past a ragged
+    // chunk's end) are skipped here.  Returns kind << 32 | id like pick().
+    auto take = [&](unsigned par, unsigned long long ready) -> unsigned long long {
+        if (!ordered) return pick(par, ready);
+        unsigned long long res = 2ULL << 32;
+        if (lane == 0) {
+            for (;;) {
+                const unsigned long long tq = atomicAdd(q.task_ctr + 2 * par, 1ULL);
+                if (tq >= NT) break;
+                const unsigned c = (unsigned)tq / per_c, slot = (unsigned)tq - c * per_c;
+                if (slot + 1 < G) {
+                    if (c < q.nchunks) {
+                        res = (unsigned long long)(c * (G - 1) + slot);
+                        break;
+                    }
+                } else if (c >= q.lag) {
+                    const unsigned cu = c - q.lag, g = slot - (G - 1);
+                    if (g * T < min(q.chunk, S - cu * q.chunk)) {
+                        res = (1ULL << 32) | (unsigned long long)(cu * R + g);
+                        break;
+                    }
+                }
+            }
+        }
+        return res;
+    };
 
 #ifdef KMC_PUSH_PROF  // thread 0's cycles per phase (experiment builds only)
     long long pt[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pc0 = clock64();
@@ -244,11 +352,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
 #endif
     long long n = p.n0, phase = p.phase0, sidx = p.sidx0;
     unsigned long long target = p.bar_base;
-    unsigned long long tbeg = 0;
     unsigned long long next = 0;
-    if (tid == 0) *next_slot = grab();
-    __syncthreads();
-    next = *next_slot;
 
     for (long long h = p.h0; h < p.h1; ++h) {
         const unsigned batch = (unsigned)(h & 1);
@@ -258,18 +362,77 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         const size_t pas = batch ? 0 : (size_t)S;         // first local row of the passive half
         const unsigned par = (unsigned)(h & 1);           // ring parity
         const unsigned long long ready = (unsigned long long)h + 1;
-        const unsigned long long tend = tbeg + NT;
         const size_t slot_bytes = kPushHeader + (size_t)q.cap * ROWB;  // one ring slot: header + cap rows
+        if (is_pub) {
+            // ---------------------------------------------------------------- the publisher: notes -> remote flags
+            // note[tp] == epoch: the store of push task tp has completed (written by its sender with release.gpu).
+            // Every thread sweeps its share with relaxed loads, pays ONE system-scope fence for what it found, sets the
+            // flags in the peers' memory and marks the notes done, until all NP flags of the half-step are out.
+            unsigned *cntp = reinterpret_cast<unsigned *>(next_slot);
+            if (tid == 0) *cntp = 0u;
+            __syncthreads();
+            const unsigned want = (unsigned)ready, done_mark = want | 0x80000000u;
+            long long t0 = 0;
+            unsigned spins = 0;
+            for (;;) {
+                unsigned found = 0;
+                for (unsigned seg = 0; seg < NP; seg += 32 * T) {  // segments of 32 notes per thread
+                    unsigned mask = 0;
+#pragma unroll 4
+                    for (unsigned k = 0; k < 32; ++k) {
+                        const unsigned tp = seg + k * T + tid;
+                        if (tp < NP) {
+                            unsigned v;  // relaxed: the fence below is the acquire for everything the sweep saw
+                            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q.notes + tp) : "memory");
+                            if (v == want) mask |= 1u << k;
+                        }
+                    }
+                    if (mask == 0) continue;
+                    // acquire for the notes seen (their senders released at GPU scope) and release for the flags below
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                    found += __popc(mask);
+                    for (; mask; mask &= mask - 1) {
+                        const unsigned tp = seg + (__ffs(mask) - 1) * T + tid, pcn = tp / (G - 1);
+                        unsigned long long *fl = q.peer_flags[(me + 1 + (tp - pcn * (G - 1))) % G] + (size_t)me * q.nchunks + pcn;
+                        asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(fl), "l"(ready) : "memory");
+                        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q.notes + tp), "r"(done_mark) : "memory");
+                    }
+                }
+                if (found) atomicAdd(cntp, found);
+                __syncthreads();
+                const unsigned total = *reinterpret_cast<volatile unsigned *>(cntp);
+                __syncthreads();
+                if (total >= NP) break;
+                if ((++spins & 0x3FFu) == 0) {  // watchdog: a lost sender must not hang the GPU
+                    if (t0 == 0) t0 = clock64();
+                    else if (clock64() - t0 > 40000000000LL) __trap();
+                }
+            }
+            next = 2ULL << 32;
+        } else {
+            if (warp == 0) {
+                if (tid == 0 && blockIdx.x == 0) {  // the other parity's counters are idle during this half-step: reset them
+                    q.task_ctr[2 * (par ^ 1)] = 0ULL;
+                    q.task_ctr[2 * (par ^ 1) + 1] = 0ULL;
+                }
+                const unsigned long long first = take(par, ready);
+                if (lane == 0) *next_slot = first;
+            }
+            __syncthreads();
+            next = *next_slot;
+        }
 
-        while (next < tend) {
-            const unsigned t = (unsigned)(next - tbeg);
+        while ((next >> 32) < 2) {
+            const unsigned kind = (unsigned)(next >> 32), t = (unsigned)next;
             unsigned long long nxt = 0;
-            if (tid == 0) nxt = grab();  // the atomic's round trip hides behind this task
-            const unsigned c = t / per_c, slot = t - c * per_c;
-            if (tid == 0) publish(false, ready);  // flags of stores that are complete by now; behind the other warps' draws
-            if (slot + 1 < G) {
+            if (ordered && warp == 0) nxt = take(par, ready);  // one atomic, no dependence on flags: issued first, used last
+            PUSH_TICK(9);
+            if (tid == 0) publish(false, ready);  // notes for the stores that are complete by now
+            PUSH_TICK(3);
+            if (kind == 0) {
                 // ------------------------------------------------------------ push(c, dest)
-                if (c < q.nchunks) {
+                const unsigned c = t / (G - 1), slot = t - c * (G - 1);
+                {
                     PUSH_TICK(9);
                     const unsigned dest = (me + 1 + slot) % G;
                     const unsigned i0 = dest * S + c * q.chunk;  // first active walker (position in its half) of the chunk
@@ -316,6 +479,10 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                     }
                     __syncthreads();
                     PUSH_TICK(0);
+                    if (warp == 0) {  // the next task: its counter reads, flag peeks and atomic run while the other warps
+                        if (!ordered) nxt = pick(par, ready);  // issue their row gathers
+                        PUSH_TICK(4);
+                    }
                     const unsigned nsend = min(tot[0], q.cap);
                     if (tid == 0) kbar_expect_tx(gbar, nsend * ROWB);
 #pragma unroll
@@ -331,17 +498,17 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                         snd->bytes = kPushHeader + nsend * ROWB;
                         snd->dst = reinterpret_cast<double *>(reinterpret_cast<unsigned char *>(q.peer_recv[dest]) +
                                                               (((size_t)par * G + me) * q.nchunks + c) * slot_bytes);
-                        snd->flag = q.peer_flags[dest] + (size_t)me * q.nchunks + c;
+                        snd->task = t;
                     }
                     PUSH_TICK(2);
 #ifdef KMC_PUSH_PROF
                     ++npush;
 #endif
                 }
-            } else if (c >= q.lag && (slot - (G - 1)) * T < min(q.chunk, S - (c - q.lag) * q.chunk)) {
-                // ------------------------------------------------------------ update(c - lag, g): one group of T walkers
+            } else if ((t % R) * T < min(q.chunk, S - (t / R) * q.chunk)) {
+                // ------------------------------------------------------------ update(cu, g): one group of T walkers
                 PUSH_TICK(9);
-                const unsigned cu = c - q.lag, g = slot - (G - 1);
+                const unsigned cu = t / R, g = t - cu * R;
                 const unsigned l0 = cu * q.chunk + g * T;     // first local position of the group
                 const unsigned rows = min(T, min(q.chunk, S - cu * q.chunk) - g * T);
                 const unsigned l = l0 + tid;
@@ -420,6 +587,11 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                 }
                 const size_t k = act + l;
                 const double lpk = live ? p.lp[k] : 0.0;
+                if (warp == 0) {  // the next task, chosen while this group's rows are on their way
+                    PUSH_TICK(7);
+                    if (!ordered) nxt = pick(par, ready);
+                    PUSH_TICK(4);
+                }
                 kbar_wait(ldbar, ldphase);
                 ldphase ^= 1;
                 if (live) {
@@ -468,6 +640,8 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
 #ifdef KMC_PUSH_PROF
                 ++nupd;
 #endif
+            } else if (warp == 0 && !ordered) {  // a round past the end of a ragged last chunk: nothing to do but to move on
+                nxt = pick(par, ready);
             }
             __syncthreads();  // everyone has read `next` of this iteration before it is overwritten
             if (tid == 0) *next_slot = nxt;
@@ -481,13 +655,14 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             ++n;
             if (++phase == p.nthin) phase = 0;
         }
+        PUSH_TICK(9);
         if (tid == 0) {  // all of this CTA's stores are complete: the last flags go out, own rows are final
             service();
             publish(true, ready);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
         }
-        tbeg = tend;
+        PUSH_TICK(3);
         if (h + 1 < p.h1) {  // the reference's join between the two sweeps (:248/:273), local to this GPU
             target += gridDim.x;
             __syncthreads();
@@ -504,8 +679,8 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
 #ifdef KMC_PUSH_PROF
     if (tid == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x / 2))
         printf("push rank %u cta %d: pushes %u update groups %u | cycles: sender %lld enum %lld gather-issue %lld | "
-               "draws %lld scan+flags %lld group %lld | handoff %lld barrier+other %lld\n",
-               me, (int)blockIdx.x, npush, nupd, pt[0], pt[1], pt[2], pt[5], pt[6], pt[7], pt[8], pt[9]);
+               "draws %lld scan+flags %lld group %lld | handoff %lld publish %lld pick %lld barrier+other %lld\n",
+               me, (int)blockIdx.x, npush, nupd, pt[0], pt[1], pt[2], pt[5], pt[6], pt[7], pt[8], pt[3], pt[4], pt[9]);
 #endif
 }
 

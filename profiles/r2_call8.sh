@@ -1,0 +1,6 @@
+set -x
+timeout 900 python -m pytest tests/test_gpu_push.py -m gpu -q 2>&1 | tail -4
+timeout 200 python profiles/push_bench.py 24 10 0p 2>&1 | tail -1
+timeout 400 python profiles/push_bench.py 24 10 0,1 0,0,0 1024,384,0 256,0,0 2>&1 | tail -3
+KMC_LIB=$PWD/build/variants/push_age1.so timeout 300 python profiles/push_bench.py 24 10 0,1 0,0,0 1024,384,0 2>&1 | tail -2
+KMC_LIB=$PWD/build/variants/push_prof.so timeout 300 python profiles/push_bench.py 24 10 0,1 0,0,0 2>&1 | tail -5

@@ -61,6 +61,8 @@ def _same(a, b):
     ("mvn10", 4096, 2, dict(push_cap=8)),                     # tiny ring slots: most rows take the owner-read fallback
     ("mvn10", 6000, 2, dict(push_chunk=384, push_lag=1)),     # ragged: S = 1500 is not a multiple of the chunk
     ("mvn10", 6000, 3, dict(push_chunk=100, push_lag=3)),     # 3 ranks, partial warps in every chunk
+    ("mvn10", 8192, 4, dict(push_lag=-1)),                    # the adaptive task hand-out (two counters)
+    ("mvn10", 6000, 2, dict(push_chunk=384, push_lag=-1)),    # adaptive, ragged
     ("rosenbrock", 2048, 2, {}),                              # d = 2 rows (16 bytes)
     ("mvn2", 1024, 4, dict(push_chunk=64)),
 ])
