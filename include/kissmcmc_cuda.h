@@ -150,7 +150,9 @@ int32_t kmc_emcee_sync(kmc_sampler_t s);
  * from the owner GPU's memory and the ranks meet at a flag barrier in peer memory per half-step.
  * kmc_emcee_ipc_export writes two 64-byte CUDA IPC handles (positions, flags); the caller
  * exchanges them (e.g. torch.distributed.all_gather) and passes all ranks' handles, rank-major,
- * to kmc_emcee_set_peers.  Then every rank calls kmc_emcee_run concurrently. */
+ * to kmc_emcee_set_peers.  Then every rank calls kmc_emcee_run(s, -1) concurrently, ONCE: the ranks only synchronise
+ * between the half-steps of one launch, so a job split over several launches returns KMC_ERR_STATE.  Superseded by the
+ * push exchange below, which has no such restriction and is faster. */
 int32_t kmc_emcee_ipc_export(kmc_sampler_t s, void *handle_x, void *handle_flags);
 int32_t kmc_emcee_set_peers(kmc_sampler_t s, const void *handles_x, const void *handles_flags, int32_t nranks,
                             int32_t rank);

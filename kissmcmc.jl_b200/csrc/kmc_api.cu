@@ -643,8 +643,8 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         else if (s->nhalf / s->scnt > kmc::kPushMaxRanks) why = "at most 8 ranks";
         else if (density->ops.batch || !density->ops.run_push) why = "a fused (non-batched) plugin with even d";
         else if (opts->mode != KMC_MODE_PHILOX || opts->launch_mode != 0) why = "Philox draws and launch_mode 0";
-        else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxChunk) why = "push_chunk in [0, 1024]";
-        else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushMaxCap) why = "push_cap in [0, 384]";
+        else if (opts->push_chunk < 0 || opts->push_chunk > kmc::kPushMaxChunk) why = "push_chunk within the kernel's maximum";
+        else if (opts->push_cap < 0 || opts->push_cap > kmc::kPushMaxCap) why = "push_cap within the kernel's maximum";
         else if (opts->push_lag < -1) why = "push_lag >= -1";
         if (why) {
             delete s;
@@ -652,16 +652,18 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
         }
         s->G = (int)(s->nhalf / s->scnt);
         s->rank = (int)(s->sbeg / s->scnt);
-        // default: a chunk sends ~256 rows per destination (a 20 KB message), at most 1024 walkers; a ring slot holds
-        // the mean hit count + 8 sigma of its binomial spread (rows past it are read from the owner directly)
+        // default: a chunk sends ~one task-width of rows per destination (kPushThreads walkers per rank), capped by the
+        // kernel's maximum chunk; a ring slot holds the mean hit count + k sigma of its binomial spread (rows past it are
+        // read from the owner directly): k = 8 for CTA-wide tasks, 3 for warp-wide ones (their shared memory is tight)
         s->chunk = opts->push_chunk > 0 ? (unsigned)opts->push_chunk
-                                        : (unsigned)std::min<long long>(kmc::kPushMaxChunk, 256LL * std::max(s->G, 1));
+                                        : (unsigned)std::min<long long>(kmc::kPushMaxChunk,
+                                                                        (long long)kmc::kPushThreads * std::max(s->G, 1));
         if (s->G == 1 && opts->push_chunk <= 0) s->chunk = kmc::kPushMaxChunk;
         s->chunk = (unsigned)std::min<long long>(s->chunk, std::max<long long>(s->scnt, 1));
         s->rounds = (s->chunk + kmc::kPushThreads - 1) / kmc::kPushThreads;
         s->nchunks = (unsigned)((s->scnt + s->chunk - 1) / s->chunk);
-        const double mean_hits = (double)s->chunk / s->G;
-        const unsigned want = (unsigned)(mean_hits + 8.0 * std::sqrt(mean_hits * (1.0 - 1.0 / s->G)) + 8.0);
+        const double mean_hits = (double)s->chunk / s->G, ksig = kmc::kPushThreads == 32 ? 3.0 : 8.0;
+        const unsigned want = (unsigned)(mean_hits + ksig * std::sqrt(mean_hits * (1.0 - 1.0 / s->G)) + 2.0);
         s->cap = opts->push_cap > 0 ? (unsigned)opts->push_cap : std::min<unsigned>(kmc::kPushMaxCap, std::max(want, 16u));
     }
     s->nstate = s->push ? 2 * s->scnt : s->nw;
@@ -925,6 +927,11 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
     if (peer) {
         if (replay || s->dn->ops.batch || s->opts.launch_mode != 0 || !s->dn->ops.run_peer)
             return fail(KMC_ERR_UNSUPPORTED, "peer mode needs a fused (non-batched) plugin, Philox draws and launch_mode 0");
+        // The ranks meet at a flag barrier BETWEEN the half-steps of one launch only: a second launch could gather from a
+        // peer that is still writing the last half-step of the first.  The pull mode therefore runs the whole job in ONE
+        // launch (the push exchange, kmc_emcee_window_*, has no such restriction).
+        if (s->npeers > 1 && (hbeg != 0 || hend != 2 * s->opts.niter_walker))
+            return fail(KMC_ERR_STATE, "peer (pull) mode runs the whole job in one launch: call kmc_emcee_run(s, -1) once");
         for (int r = 0; r < s->npeers; ++r) {
             p.peer_x[r] = s->peer_x[r];
             p.peer_flags[r] = s->peer_flags[r];
@@ -955,7 +962,7 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
         q.cap = s->cap;
         q.lag = s->lag;
         q.batch = 1;
-        q.age = 1;
+        q.age = 2;
         if (const char *e = getenv("KMC_PUSH_BATCH")) q.batch = (unsigned)std::max(1, std::min(6, atoi(e)));  // profiling knobs
         if (const char *e = getenv("KMC_PUSH_AGE")) q.age = (unsigned)std::max(1, std::min(3, atoi(e)));
         set_range(hbeg, hend);

@@ -405,6 +405,16 @@ static __global__ void __launch_bounds__(max_threads<D>(), min_blocks<D>()) emce
 //   * each thread gathers its partner row with one bulk request (from the owner GPU in peer mode).
 // Own-row buffers are double-buffered so the store of group g overlaps the loads of group g+1.
 constexpr int kBulkThreads = 256;
+// KMC_BULK_STORE_ALL = 1: the CTA's own rows go back as ONE bulk store per group (rows that were not accepted are
+// rewritten with their old value).  0 (default): only ACCEPTED rows are written, straight from registers -- the kernel is
+// bound by its DRAM traffic and at the ~30 % acceptance of the 10-D Gaussian that removes ~50 of 368 bytes per walker-step
+// (the partially covered sector at a row's end merges in L2 with the line the group's own-row load has just brought in).
+#ifndef KMC_BULK_STORE_ALL
+#define KMC_BULK_STORE_ALL 0
+#endif
+#ifndef KMC_BULK_CTAS
+#define KMC_BULK_CTAS 3
+#endif
 
 __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsigned bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst),
@@ -414,7 +424,7 @@ __device__ __forceinline__ void bulk_s2g(void *gdst, const void *smem_src, unsig
 }
 
 template <template <int> class Dn, int D, bool PEER>
-static __global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
+static __global__ void __launch_bounds__(kBulkThreads, KMC_BULK_CTAS) emcee_bulk_kernel(const RunParams p, const Dn<D> dn) {
     static_assert(D % 2 == 0, "rows must be multiples of 16 bytes");
     extern __shared__ __align__(128) unsigned char bulk_smem[];
     constexpr unsigned T = kBulkThreads, ROWB = D * 8;
@@ -489,17 +499,23 @@ static __global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(cons
                 else if (tt < -(double)p.margin) acc = false;
                 else acc = accept_slow<false, false>(p, h, base + l, z, p1, lpk);
                 if (acc) {  // :261-265
+#if KMC_BULK_STORE_ALL
 #pragma unroll
                     for (int c = 0; c < D; c += 2)
                         *reinterpret_cast<double2 *>(own + (size_t)tid * D + c) = make_double2(y[c], y[c + 1]);
+#else
+                    store_row<D>(p.x + k * D, y);
+#endif
                     p.lp[k] = p1;
                     p.nacc[k] += 1u;
                 }
                 if (store) chain_store<D>(p, chain_row(p, sidx, batch, base + l), acc, y, xk, p1, lpk);
             }
+#if KMC_BULK_STORE_ALL
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> bulk store
             __syncthreads();
             if (tid == 0) bulk_s2g(p.x + (a0 + base + (size_t)g * T) * D, own, rows * ROWB);
+#endif
         }
         if (batch == 1) {
             if (n == 0) {  // :285-288
@@ -512,10 +528,14 @@ static __global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(cons
             ++n;
             if (++phase == p.nthin) phase = 0;
         }
+#if KMC_BULK_STORE_ALL
         if (tid == 0) {  // all of this CTA's row stores are complete and ordered before the barrier
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             asm volatile("fence.proxy.async;" ::: "memory");
         }
+#else
+        asm volatile("fence.proxy.async;" ::: "memory");  // this thread's row stores (generic proxy) before the other CTAs' bulk gathers
+#endif
         if (h + 1 < p.h1) {
             target += gridDim.x;
             __syncthreads();
@@ -525,6 +545,9 @@ static __global__ void __launch_bounds__(kBulkThreads, 3) emcee_bulk_kernel(cons
                 if (tid == 0) barrier_wait(p.barrier, target);
                 __syncthreads();
             }
+#if !KMC_BULK_STORE_ALL
+            asm volatile("fence.proxy.async;" ::: "memory");  // acquired row stores -> this thread's bulk gathers
+#endif
             if constexpr (PEER) {
                 if (blockIdx.x == 0) cross_gpu_barrier(p, p.epoch_base + (unsigned long long)(h - p.h0) + 1);
                 target += gridDim.x;

@@ -21,8 +21,8 @@
 //                   in the owner's message.  Waits for the G-1 chunk flags, then one group of the bulk kernel's loop
 //                   (kmc_kernels.cuh, emcee_bulk_kernel): own rows in one bulk load, partner rows gathered from the
 //                   local receive ring (remote owner), the local passive shard (own rows) or, for the rare row past
-//                   the ring slot's capacity, straight from the owner's memory; accept / update / chain store; own rows
-//                   back in one bulk store.
+//                   the ring slot's capacity, straight from the owner's memory; accept / chain store; ACCEPTED rows are
+//                   written back from registers (the update side is bound by its DRAM traffic).
 //
 // Two hand-outs (PushParams::lag): ORDERED (the default) -- one counter, the pushes of chunk c, then the update groups
 // of chunk c - lag; the next task id is ONE atomic issued at the start of the current task, so handing out costs nothing;
@@ -66,14 +66,18 @@ namespace kmc {
 #define KMC_PUSH_THREADS 256
 #endif
 #ifndef KMC_PUSH_CTAS
-#define KMC_PUSH_CTAS 3
+#define KMC_PUSH_CTAS (KMC_PUSH_THREADS == 32 ? 20 : 3)
 #endif
 constexpr int kPushThreads = KMC_PUSH_THREADS;
 constexpr int kPushWarps = kPushThreads / 32;
-constexpr int kPushMaxChunk = 1024;
-constexpr int kPushMaxRounds = kPushMaxChunk / kPushThreads;  // rounds of T walkers per chunk
+// T = 256: a task is a CTA of 8 warps (chunks of up to 4 rounds, barriers between its phases).  T = 32: a task is ONE
+// WARP (chunks of up to 8 rounds): ~20 independent task streams per SM instead of 3 hide each other's latencies -- a
+// 32-thread CTA's __syncthreads is free.
+constexpr int kPushMaxRounds = kPushThreads == 32 ? 8 : 1024 / kPushThreads;  // rounds of T walkers per chunk
+constexpr int kPushMaxChunk = kPushMaxRounds * kPushThreads;
 constexpr int kPushMaxRanks = 8;
-constexpr int kPushSlots = 32;  // (round, warp) slots of a chunk = one warp's lanes (prefix by shuffles)
+constexpr int kPushSlots = kPushMaxRounds * kPushWarps;  // (round, warp) slots of a chunk <= one warp's lanes (prefix by shuffles)
+constexpr int kPushPublishers = kPushThreads == 32 ? 8 : 1;  // CTAs that publish flags instead of taking tasks
 constexpr int kPushFifo = 8;    // flags whose store is issued but which are not published yet
 #ifndef KMC_PUSH_BATCH
 #define KMC_PUSH_BATCH 1
@@ -83,7 +87,7 @@ constexpr unsigned kPushBatch = KMC_PUSH_BATCH;  // flags published per system-s
 #define KMC_PUSH_AGE 3
 #endif
 constexpr unsigned kPushAge = KMC_PUSH_AGE;      // a flag is published once its store is this many commits old
-static_assert(kPushMaxRounds * kPushWarps == kPushSlots, "slots = rounds x warps = one warp's lanes");
+static_assert(kPushSlots <= 32, "the slot prefix is one warp's shuffle scan");
 
 struct PushParams {
     double *recv;               // local receive ring [2 parities][G sources][nchunks][cap][D]
@@ -103,8 +107,9 @@ struct PushParams {
     unsigned batch;    // notes posted per GPU-scope fence (>= 1)
     unsigned age;      // a store is taken for complete once it is this many commits old (1..3)
 };
-constexpr int kPushMaxCap = 384;   // rows: the message buffer is 16 + cap * 8D bytes of shared memory
-constexpr int kPushHeader = 16;    // bytes: 4 x u32, the message row at which each round of the chunk starts
+constexpr int kPushMaxCap = kPushThreads == 32 ? 64 : 384;  // rows: the message buffer is header + cap * 8D bytes of shared memory
+constexpr int kPushHeader = 4 * kPushMaxRounds;  // bytes: the message row at which each round of the chunk starts (u32 each)
+static_assert(kPushHeader % 16 == 0, "bulk copies move multiples of 16 bytes");
 
 // The sender's state: touched by thread 0 only, kept in shared memory so that it costs the other 255 threads no registers.
 struct PushSender {
@@ -112,8 +117,8 @@ struct PushSender {
     unsigned task;                   // its push task id (names the note and the flag)
     unsigned pending, bytes;
     unsigned gphase;                 // phase of gbar
-    unsigned ncommit;                // bulk store groups committed so far
-    unsigned own_commit, msg_commit; // commit index of the last store that reads the own-row / the message buffer
+    unsigned ncommit;                // tasks this CTA has started (the sender's clock)
+    unsigned msg_commit, pad0;       // the clock when the newest message store was issued
     unsigned fhead, ftail;           // fifo[fhead..ftail): flags of issued stores that are not published yet
 };
 
@@ -178,7 +183,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     unsigned *cnt = reinterpret_cast<unsigned *>(ldbar + 4 + kPushFifo);  // [kPushSlots][kPushMaxRanks] hits per slot, owner
     unsigned *pre = cnt + kPushSlots * kPushMaxRanks;     // exclusive prefix of cnt over the slots, per owner
     unsigned *tot = pre + kPushSlots * kPushMaxRanks;     // [kPushMaxRanks] totals
-    unsigned *fidx = tot + kPushMaxRanks;                 // [kPushFifo] commit index of the store behind fifo[k]
+    unsigned *fidx = tot + kPushMaxRanks;                 // [kPushFifo] (spare)
 
     const unsigned tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const unsigned S = q.S, me = q.rank, G = q.G, R = q.rounds;
@@ -187,23 +192,22 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     const bool ordered = q.lag > 0;           // one counter, fixed order: pushes of chunk c, then the update groups of chunk c - lag
     const unsigned per_c = G - 1 + R;
     const unsigned NT = (q.nchunks + q.lag) * per_c;
-    const bool use_pub = G > 1 && gridDim.x > 1;                   // the last CTA publishes flags and takes no tasks
-    const bool is_pub = use_pub && blockIdx.x == gridDim.x - 1;
+    // the last kPushPublishers CTAs publish flags and take no tasks (each its slice of the push tasks' notes)
+    const bool use_pub = G > 1 && gridDim.x > (unsigned)kPushPublishers;
+    const bool is_pub = use_pub && blockIdx.x >= gridDim.x - kPushPublishers;
     if (tid == 0) {
         kbar_init(ldbar, 1);
         kbar_init(gbar, 1);
-        snd->pending = snd->gphase = snd->ncommit = snd->own_commit = snd->msg_commit = snd->fhead = snd->ftail = 0u;
+        snd->pending = snd->gphase = snd->ncommit = snd->msg_commit = snd->fhead = snd->ftail = 0u;
     }
     __syncthreads();
     unsigned ldphase = 0;
 
     // ------------------------------------------------------------------ the sender (thread 0)
+    // The only bulk async-groups of this thread are the message stores, one per push, in order.
     // snd->pending: a push whose gathers are in flight into `msg` and whose store is not issued yet.
-    // fifo[fhead..ftail): flags of issued stores; fidx[k]: the commit index of the store behind fifo[k].
-    auto commit = [&]() {
-        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        snd->ncommit += 1;
-    };
+    // fifo[fhead..ftail): push task ids of issued stores whose notes are not posted yet; snd->ncommit counts the CTA's
+    // tasks (a clock), snd->msg_commit is its value when the newest store was issued.
     // issue the bulk store of the pending push (its gathers have landed by now: they were issued a task ago)
     auto service = [&]() {
         if (!snd->pending) return;
@@ -213,42 +217,33 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(snd->dst),
                      "r"((unsigned)__cvta_generic_to_shared(msg)), "r"(snd->bytes)
                      : "memory");
-        commit();
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         snd->msg_commit = snd->ncommit;
         const unsigned ft = snd->ftail;
         fifo[ft % kPushFifo] = snd->task;
-        fidx[ft % kPushFifo] = snd->ncommit;
         snd->ftail = ft + 1;
         snd->pending = 0;
     };
-    // publish the flags whose stores are complete: one system-scope fence for the whole batch
+    // post the notes (or, without a publisher, set the flags) of the stores that are complete.  A message drains into
+    // NVLink at the link's pace and completion can only be WAITED for, so by default only what can be had without
+    // blocking is taken: everything but the newest store (wait_group 1), or everything once the newest store is `age`
+    // tasks old (wait_group 0 then returns at once, barring a congested link).
     auto publish = [&](bool all, unsigned long long ready) {
         unsigned fhead = snd->fhead;
-        const unsigned ftail = snd->ftail, ncommit = snd->ncommit;
+        const unsigned ftail = snd->ftail;
         if (fhead == ftail) return;
-        unsigned upto = fhead;
-        if (all) {
+        unsigned upto;
+        if (all || snd->ncommit - snd->msg_commit >= q.age || ftail - fhead >= kPushFifo - 1) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
             upto = ftail;
         } else {
-            // a message drains into NVLink at the link's pace: only stores at least kPushAge commits old are taken
-            // (wait_group kPushAge then returns at once, barring a congested link)
-            while (upto != ftail && fidx[upto % kPushFifo] + q.age <= ncommit) ++upto;
-            if (upto - fhead < q.batch && ftail - fhead < kPushFifo - 1) return;  // batch not worth a fence yet
-            if (upto == fhead) {  // queue full of young stores: wait for all of them
-                asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-                upto = ftail;
-            } else if (q.age >= 3) {
-                asm volatile("cp.async.bulk.wait_group 3;" ::: "memory");
-            } else if (q.age == 2) {
-                asm volatile("cp.async.bulk.wait_group 2;" ::: "memory");
-            } else {
-                asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
-            }
+            if (ftail - fhead < 1 + q.batch) return;
+            asm volatile("cp.async.bulk.wait_group 1;" ::: "memory");
+            upto = ftail - 1;
         }
         // wait_group made the completed stores' writes visible to this thread (completion of a bulk async-group implies
-        // the generic-async proxy fence); the release fence then orders them before the flags for every observer.  No
-        // fence.proxy.async here: it would also wait for the YOUNGER message that is still draining into the link
+        // the generic-async proxy fence); the release fence then orders them before the note / flag for every observer.
+        // No fence.proxy.async here: it would also wait for the YOUNGER message that is still draining into the link
         // (measured: ~20k cycles per publish, a quarter of the kernel).
         if (use_pub) {  // hand the completed stores to the publisher CTA: release at GPU scope is all a worker pays
             asm volatile("fence.acq_rel.gpu;" ::: "memory");
@@ -256,7 +251,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                 asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q.notes + (unsigned)fifo[fhead % kPushFifo]),
                              "r"((unsigned)ready)
                              : "memory");
-        } else {  // a one-CTA grid has no publisher: set the remote flags directly
+        } else {  // a grid too small for a publisher: set the remote flags directly
             asm volatile("fence.acq_rel.sys;" ::: "memory");
             for (; fhead != upto; ++fhead) {
                 const unsigned tp = (unsigned)fifo[fhead % kPushFifo], pcn = tp / (G - 1);
@@ -266,16 +261,8 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         }
         snd->fhead = fhead;
     };
-    // before a shared-memory buffer is overwritten: the last bulk store that reads it has finished READING it.  Bulk
-    // groups complete in order, so it is enough that at most (groups committed after that store) are still pending --
-    // an update group must not wait for a message that is still draining into NVLink, nor a push for own-row stores.
-    auto wait_read = [&](unsigned allowed) {
-        if (allowed == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        else if (allowed == 1) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-        else asm volatile("cp.async.bulk.wait_group.read 2;" ::: "memory");
-    };
-    auto own_free = [&]() { wait_read(snd->ncommit - snd->own_commit); };
-    auto msg_free = [&]() { wait_read(snd->ncommit - snd->msg_commit); };
+    // before the message buffer is overwritten: the previous message has left shared memory
+    auto msg_free = [&]() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); };
 
     // The next task of this CTA, chosen by warp 0 (all 32 lanes call it; the result is valid in lane 0):
     // kind << 32 | id, kind 0 = push, 1 = update, 2 = nothing left.  An update group whose chunk's flags are all set
@@ -371,17 +358,20 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             unsigned *cntp = reinterpret_cast<unsigned *>(next_slot);
             if (tid == 0) *cntp = 0u;
             __syncthreads();
+            const unsigned pubi = blockIdx.x - (gridDim.x - kPushPublishers);             // this publisher's slice of the notes
+            const unsigned plo = (unsigned)((unsigned long long)NP * pubi / kPushPublishers);
+            const unsigned phi = (unsigned)((unsigned long long)NP * (pubi + 1) / kPushPublishers);
             const unsigned want = (unsigned)ready, done_mark = want | 0x80000000u;
             long long t0 = 0;
             unsigned spins = 0;
             for (;;) {
                 unsigned found = 0;
-                for (unsigned seg = 0; seg < NP; seg += 32 * T) {  // segments of 32 notes per thread
+                for (unsigned seg = plo; seg < phi; seg += 32 * T) {  // segments of 32 notes per thread
                     unsigned mask = 0;
 #pragma unroll 4
                     for (unsigned k = 0; k < 32; ++k) {
                         const unsigned tp = seg + k * T + tid;
-                        if (tp < NP) {
+                        if (tp < phi) {
                             unsigned v;  // relaxed: the fence below is the acquire for everything the sweep saw
                             asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(q.notes + tp) : "memory");
                             if (v == want) mask |= 1u << k;
@@ -402,7 +392,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                 __syncthreads();
                 const unsigned total = *reinterpret_cast<volatile unsigned *>(cntp);
                 __syncthreads();
-                if (total >= NP) break;
+                if (total >= phi - plo) break;
                 if ((++spins & 0x3FFu) == 0) {  // watchdog: a lost sender must not hang the GPU
                     if (t0 == 0) t0 = clock64();
                     else if (clock64() - t0 > 40000000000LL) __trap();
@@ -427,7 +417,10 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             unsigned long long nxt = 0;
             if (ordered && warp == 0) nxt = take(par, ready);  // one atomic, no dependence on flags: issued first, used last
             PUSH_TICK(9);
-            if (tid == 0) publish(false, ready);  // notes for the stores that are complete by now
+            if (tid == 0) {
+                snd->ncommit += 1;
+                publish(false, ready);  // notes for the stores that are complete by now
+            }
             PUSH_TICK(3);
             if (kind == 0) {
                 // ------------------------------------------------------------ push(c, dest)
@@ -460,21 +453,21 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                     __syncthreads();
                     PUSH_TICK(1);
                     if (warp == 0) {
-                        const unsigned v = cnt[lane];
+                        const unsigned v = lane < (unsigned)kPushSlots ? cnt[lane] : 0u;
                         unsigned incl = v;
 #pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
+                        for (int o = 1; o < kPushSlots; o <<= 1) {
                             const unsigned u = __shfl_up_sync(0xffffffffu, incl, o);
                             if ((int)lane >= o) incl += u;
                         }
-                        pre[lane] = incl - v;
-                        if (lane == 31) tot[0] = incl;
+                        if (lane < (unsigned)kPushSlots) pre[lane] = incl - v;
+                        if (lane == kPushSlots - 1) tot[0] = incl;
                         if (lane == 0) {  // the sender: the previous push goes out, then the message buffer is free again
                             service();
                             msg_free();
                         }
                         __syncwarp();
-                        if ((lane % kPushWarps) == 0)  // header: the message row at which each round starts
+                        if (lane < (unsigned)kPushSlots && (lane % kPushWarps) == 0)  // header: the row at which each round starts
                             reinterpret_cast<unsigned *>(msg)[lane / kPushWarps] = incl - v;
                     }
                     __syncthreads();
@@ -548,10 +541,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                         }
                         if (lane < (unsigned)kPushWarps) pre[lane * kPushMaxRanks + o] = incl - v;
                     }
-                    if (lane == 0) {
-                        service();
-                        own_free();  // the previous group's own-row store has read its source
-                    }
+                    if (lane == 0) service();
                     // every source's rows of this chunk must have landed in my ring (flags are set after the stores).
                     // No flag of mine may stay unpublished while I wait for somebody else's (two CTAs on two GPUs could
                     // otherwise wait for each other's deferred flags): publish everything before blocking.
@@ -614,10 +604,8 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                     if (tt > (double)p.margin) acc = true;
                     else if (tt < -(double)p.margin) acc = false;
                     else acc = accept_slow<false, false>(p, h, me * S + l, z, p1, lpk);
-                    if (acc) {  // :261-265
-#pragma unroll
-                        for (int cc = 0; cc < D; cc += 2)
-                            *reinterpret_cast<double2 *>(ownb + (size_t)tid * D + cc) = make_double2(y[cc], y[cc + 1]);
+                    if (acc) {  // :261-265: only accepted rows are written (the kernel is bound by its DRAM traffic)
+                        store_row<D>(p.x + k * D, y);
                         p.lp[k] = p1;
                         if (!reset) p.nacc[k] += 1u;
                     }
@@ -626,15 +614,6 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                         p.nacc[(size_t)S + l] = 0u;
                     }
                     if (store) chain_store<D>(p, chain_row(p, sidx, batch, me * S + l), acc, y, xk, p1, lpk);
-                }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // smem writes -> bulk store
-                __syncthreads();
-                if (tid == 0) {
-                    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p.x + (act + l0) * D),
-                                 "r"((unsigned)__cvta_generic_to_shared(ownb)), "r"(rows * ROWB)
-                                 : "memory");
-                    commit();
-                    snd->own_commit = snd->ncommit;
                 }
                 PUSH_TICK(7);
 #ifdef KMC_PUSH_PROF
@@ -656,12 +635,12 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
             if (++phase == p.nthin) phase = 0;
         }
         PUSH_TICK(9);
-        if (tid == 0) {  // all of this CTA's stores are complete: the last flags go out, own rows are final
+        if (tid == 0) {  // all of this CTA's messages are complete: the last notes go out
             service();
             publish(true, ready);
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            asm volatile("fence.proxy.async;" ::: "memory");
         }
+        asm volatile("fence.proxy.async;" ::: "memory");  // this thread's row stores (generic proxy) before anybody's bulk gathers
         PUSH_TICK(3);
         if (h + 1 < p.h1) {  // the reference's join between the two sweeps (:248/:273), local to this GPU
             target += gridDim.x;
@@ -673,6 +652,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
                 }
                 __syncthreads();
             }
+            asm volatile("fence.proxy.async;" ::: "memory");  // acquired row stores -> this thread's bulk gathers
         }
         PUSH_TICK(9);
     }
