@@ -70,9 +70,11 @@ namespace kmc {
 #endif
 constexpr int kPushThreads = KMC_PUSH_THREADS;
 constexpr int kPushWarps = kPushThreads / 32;
-// T = 256: a task is a CTA of 8 warps (chunks of up to 4 rounds, barriers between its phases).  T = 32: a task is ONE
-// WARP (chunks of up to 8 rounds): ~20 independent task streams per SM instead of 3 hide each other's latencies -- a
-// 32-thread CTA's __syncthreads is free.
+// T = 256 (the build default): a task is a CTA of 8 warps (chunks of up to 4 rounds, barriers between its phases).
+// T = 32 (-DKMC_PUSH_THREADS=32): a task is ONE WARP (chunks of up to 8 rounds), ~20 independent task streams per SM
+// instead of 3.  Measured SLOWER (2 B200s, 2^24 x 10-D: 0.59-0.63 vs 0.47 ms per half-step, profiles/r2_summary.md): the
+// update groups run at the memory system's pace either way (~17 cycles per walker-step and SM, like the single-GPU bulk
+// kernel), so more streams only add per-task overhead.
 constexpr int kPushMaxRounds = kPushThreads == 32 ? 8 : 1024 / kPushThreads;  // rounds of T walkers per chunk
 constexpr int kPushMaxChunk = kPushMaxRounds * kPushThreads;
 constexpr int kPushMaxRanks = 8;
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
     const unsigned NU = q.nchunks * R;        // update tasks per half-step: (chunk, round of T walkers)
     const bool ordered = q.lag > 0;           // one counter, fixed order: pushes of chunk c, then the update groups of chunk c - lag
     const unsigned per_c = G - 1 + R;
-    const unsigned NT = (q.nchunks + q.lag) * per_c;
+    const unsigned long long NT_dense = (unsigned long long)q.nchunks * per_c;  // every push and every update group once
     // the last kPushPublishers CTAs publish flags and take no tasks (each its slice of the push tasks' notes)
     const bool use_pub = G > 1 && gridDim.x > (unsigned)kPushPublishers;
     const bool is_pub = use_pub && blockIdx.x >= gridDim.x - kPushPublishers;
@@ -302,29 +304,26 @@ __global__ void __launch_bounds__(kPushThreads, KMC_PUSH_CTAS) emcee_push_kernel
         return res;
     };
 
-    // ORDERED hand-out: sequence number t -> chunk index c = t / (G-1+R); its first G-1 slots are the pushes of chunk c,
-    // the next R the update groups of chunk c - lag.  Slots that fall outside (c >= nchunks, c < lag, a round past a ragged
-    // chunk's end) are skipped here.  Returns kind << 32 | id like pick().
+    // ORDERED hand-out: ONE atomic per task.  The sequence "pushes of chunk index c, then the update groups of chunk c - lag"
+    // has three regions -- c < lag: pushes only; lag <= c < nchunks: pushes and updates; nchunks <= c < nchunks + lag:
+    // updates only -- numbered densely, so no sequence number is wasted on a slot that holds no task (a CTA that had to
+    // skip the 7 empty push slots between two updates of the tail paid 7 dependent atomics for one task).
+    // Returns kind << 32 | id like pick().
     auto take = [&](unsigned par, unsigned long long ready) -> unsigned long long {
         if (!ordered) return pick(par, ready);
         unsigned long long res = 2ULL << 32;
         if (lane == 0) {
-            for (;;) {
-                const unsigned long long tq = atomicAdd(q.task_ctr + 2 * par, 1ULL);
-                if (tq >= NT) break;
-                const unsigned c = (unsigned)tq / per_c, slot = (unsigned)tq - c * per_c;
-                if (slot + 1 < G) {
-                    if (c < q.nchunks) {
-                        res = (unsigned long long)(c * (G - 1) + slot);
-                        break;
-                    }
-                } else if (c >= q.lag) {
-                    const unsigned cu = c - q.lag, g = slot - (G - 1);
-                    if (g * T < min(q.chunk, S - cu * q.chunk)) {
-                        res = (1ULL << 32) | (unsigned long long)(cu * R + g);
-                        break;
-                    }
-                }
+            const unsigned long long v = atomicAdd(q.task_ctr + 2 * par, 1ULL);
+            const unsigned long long lenA = (unsigned long long)q.lag * (G - 1);
+            const unsigned long long lenB = (unsigned long long)(q.nchunks - q.lag) * per_c;
+            if (v < lenA) {
+                res = v;  // push(c, slot) with id = c * (G-1) + slot = v
+            } else if (v < lenA + lenB) {
+                const unsigned w = (unsigned)(v - lenA), c = q.lag + w / per_c, slot = w % per_c;
+                if (slot + 1 < G) res = (unsigned long long)(c * (G - 1) + slot);
+                else res = (1ULL << 32) | (unsigned long long)((c - q.lag) * R + (slot - (G - 1)));
+            } else if (v < NT_dense) {
+                res = (1ULL << 32) | (unsigned long long)((q.nchunks - q.lag) * R + (unsigned)(v - lenA - lenB));
             }
         }
         return res;

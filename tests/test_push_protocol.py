@@ -14,14 +14,14 @@ T = 256          # kPushThreads
 WARPS = T // 32
 
 
-def _const(name):
-    return int(re.search(rf"constexpr int {name} = (\d+)", SRC).group(1))
-
-
 def test_constants_the_model_assumes():
+    """The model below is written for the build default: CTA-wide tasks of 256 threads, chunks of up to 4 rounds."""
     assert re.search(r"#define KMC_PUSH_THREADS (\d+)", SRC).group(1) == str(T)
-    assert _const("kPushMaxChunk") == 1024 and _const("kPushSlots") == 32 and _const("kPushMaxRanks") == 8
-    assert _const("kPushHeader") == 16 and _const("kPushMaxCap") * 16 * 8 + 16 + 2 * T * 16 * 8 < 227 * 1024  # d = 16 fits
+    assert "kPushMaxRounds = kPushThreads == 32 ? 8 : 1024 / kPushThreads" in SRC      # 4 rounds of 256 = 1024 walkers
+    assert "kPushHeader = 4 * kPushMaxRounds" in SRC                                   # one u32 per round
+    assert re.search(r"constexpr int kPushMaxRanks = (\d+)", SRC).group(1) == "8"
+    max_cap = int(re.search(r"kPushMaxCap = kPushThreads == 32 \? (\d+) : (\d+)", SRC).group(2))
+    assert max_cap == 384 and 2 * T * 16 * 8 + 16 + max_cap * 16 * 8 < 227 * 1024     # d = 16 fits one CTA's shared memory
 
 
 def sender_pack(owner_of, me, chunk, cap):
@@ -56,33 +56,47 @@ def test_sender_packing_equals_receiver_arithmetic(G, chunk, cap):
                 assert receiver_row(owner_of, off, header) == cap + k >= cap
 
 
-def task_of(t, G, R, nchunks, lag):
-    """Task id -> ("push", c, slot) | ("update", c - lag, g) | None, exactly the kernel's decode."""
+def task_of(v, G, R, nchunks, lag):
+    """Dense ordered sequence number -> ("push", c, slot) | ("update", c, g), exactly the kernel's take():
+    region A (chunk index < lag) holds pushes only, region B pushes and the update groups of chunk c - lag, region C
+    (chunk index >= nchunks) update groups only -- no sequence number is spent on an empty slot."""
     per_c = G - 1 + R
-    c, slot = divmod(t, per_c)
-    if slot + 1 < G:
-        return ("push", c, slot) if c < nchunks else None
-    g = slot - (G - 1)
-    return ("update", c - lag, g) if c >= lag else None
+    len_a, len_b = lag * (G - 1), (nchunks - lag) * per_c
+    if v < len_a:
+        return ("push",) + divmod(v, G - 1)
+    if v < len_a + len_b:
+        w = v - len_a
+        c, slot = lag + w // per_c, w % per_c
+        if slot + 1 < G:
+            return ("push", c, slot)
+        return ("update", c - lag, slot - (G - 1))
+    if v < nchunks * per_c:
+        u = (nchunks - lag) * R + (v - len_a - len_b)
+        return ("update",) + divmod(u, R)
+    return None
 
 
-@pytest.mark.parametrize("G,R,nchunks,lag", [(2, 2, 40, 7), (8, 4, 33, 33), (4, 4, 17, 1), (3, 1, 9, 3), (1, 4, 12, 5)])
+@pytest.mark.parametrize("G,R,nchunks,lag", [(2, 2, 40, 7), (8, 4, 33, 33), (4, 4, 17, 1), (3, 1, 9, 3), (1, 4, 12, 5),
+                                             (8, 4, 1024, 320), (2, 2, 5, 5)])
 def test_task_order_covers_everything_once_and_never_waits_upwards(G, R, nchunks, lag):
     per_c = G - 1 + R
-    NT = (nchunks + lag) * per_c
+    NT = nchunks * per_c
+    assert task_of(NT, G, R, nchunks, lag) is None
     pushes, updates = {}, {}
     for t in range(NT):
         k = task_of(t, G, R, nchunks, lag)
-        if k is None:
-            continue
+        assert k is not None                                 # one atomic per task: no empty slots
         (pushes if k[0] == "push" else updates)[k[1:]] = t
     assert sorted(pushes) == [(c, s) for c in range(nchunks) for s in range(G - 1)]
     assert sorted(updates) == [(c, g) for c in range(nchunks) for g in range(R)]
-    # an update of chunk c waits for the pushes of chunk c on the OTHER ranks, which carry the same task ids there:
-    # every one of them precedes the update in the (identical) task order -> waits only point downwards
+    # an update of chunk c waits for the pushes of chunk c on the OTHER ranks, which carry the same sequence numbers
+    # there: every one of them precedes the update in the (identical) order -> waits only point downwards; and the
+    # updates trail the pushes by `lag` chunks where both run
     for (c, g), tu in updates.items():
         for s in range(G - 1):
             assert pushes[(c, s)] < tu
+            if c + lag < nchunks:
+                assert pushes[(c + lag, s)] < tu
     # every destination is served exactly once per chunk: dest = (me + 1 + slot) % G for slot in 0..G-2
     for me in range(G):
         assert sorted((me + 1 + s) % G for s in range(G - 1)) == [r for r in range(G) if r != me]
