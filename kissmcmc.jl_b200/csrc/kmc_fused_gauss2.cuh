@@ -1,5 +1,6 @@
 // kmc_fused_gauss2.cuh -- K2G: the fused dense-Gaussian half-step (K2F, kmc_fused_gauss.cuh) with the MATRIX as the
-// TMEM-resident A operand of the tcgen05 GEMM.  OPT-IN (set_option("fused_variant", 2)); K2F stays the default.
+// TMEM-resident A operand of the tcgen05 GEMM.  The DEFAULT fused kernel of the tensor-core dense Gaussian in launch_mode 0
+// (kmc_density_s::fused_variant = 2); set_option("fused_variant", 1) selects K2F.
 //
 // Why.  K2F keeps the three matrix pieces (96 KB) and one tile of walker pieces (96 KB) in shared memory, so a tile's
 // phases are serialised (no room for a second walker-piece buffer) and every SS-mode MMA reads 7.5 KB of operands from
