@@ -17,15 +17,18 @@ import warnings
 import numpy as np
 
 
-def acor1d(x, norm: bool = True) -> np.ndarray:
-    """Autocorrelation function of one chain via FFT, NO zero padding (circular), first half kept (:252-273)."""
+def acor1d(x, norm: bool = True, zero_pad: bool = False) -> np.ndarray:
+    """Autocorrelation function of one chain via FFT, first half kept (:252-273).  Like the reference there is NO zero
+    padding by default (the correlation is circular, which biases tau for chains that are short against tau);
+    zero_pad=True pads to 2n, the linear autocorrelation -- a deliberate extension, not reference behaviour."""
     x = np.asarray(x, dtype=np.float64)
-    f = np.fft.fft(x - x.mean())
-    acf = np.real(np.fft.ifft(f * np.conj(f)))
-    acf /= 4 * len(x)
+    n = len(x)
+    f = np.fft.fft(x - x.mean(), n=2 * n if zero_pad else n)
+    acf = np.real(np.fft.ifft(f * np.conj(f)))[:n]
+    acf /= 4 * n
     if norm:
         acf /= acf[0]
-    return acf[:len(acf) // 2]
+    return acf[:n // 2]
 
 
 def auto_window(taus, c) -> int:
@@ -36,31 +39,33 @@ def auto_window(taus, c) -> int:
     return len(taus) - 1
 
 
-def _mean_rho_torch(th):
+def _mean_rho_torch(th, zero_pad=False):
     """Chain-averaged normalised autocorrelation for every parameter on the GPU (batched FFT over
     all chains and parameters at once): th [nchains, nsamples, ntheta] torch tensor -> [ntheta, nsamples//2]."""
     import torch
     x = th.to(torch.float64)
     x = x - x.mean(dim=1, keepdim=True)
-    f = torch.fft.fft(x, dim=1)
-    acf = torch.fft.ifft(f * torch.conj(f), dim=1).real / (4 * x.shape[1])
+    n = x.shape[1]
+    f = torch.fft.fft(x, n=2 * n if zero_pad else n, dim=1)
+    acf = torch.fft.ifft(f * torch.conj(f), dim=1).real[:, :n, :] / (4 * n)
     acf = acf / acf[:, :1, :]
     return acf[:, :x.shape[1] // 2, :].mean(dim=0).T.contiguous()
 
 
-def int_acorr(thetas, c=5, warn=True, warnat=50):
+def int_acorr(thetas, c=5, warn=True, warnat=50, zero_pad=False):
     """Integrated autocorrelation time per parameter, averaged over chains (:140-167).
 
     thetas: [nchains, nsamples] or [nchains, nsamples, ntheta]; a numpy array (host FFT, chain by
     chain like the reference) or a torch tensor (one batched FFT on its device).
     Returns (tau[ntheta], converged[ntheta]); converged = nsamples / tau should be > ~50.
-    If anything is NaN both are set to -1 (the reference's "hack")."""
+    If anything is NaN both are set to -1 (the reference's "hack").  zero_pad: see acor1d (default: the reference's
+    circular correlation)."""
     assert c > 1
     rho_dev = None
     if type(thetas).__module__.startswith("torch"):      # device chains: one batched FFT on the GPU
         tt = thetas if thetas.ndim == 3 else thetas[:, :, None]
         nchains, nsamples, ntheta = tt.shape
-        rho_dev = _mean_rho_torch(tt).cpu().numpy()
+        rho_dev = _mean_rho_torch(tt, zero_pad).cpu().numpy()
     else:
         th = np.asarray(thetas, dtype=np.float64)
         if th.ndim == 2:
@@ -73,7 +78,7 @@ def int_acorr(thetas, c=5, warn=True, warnat=50):
         else:
             rho = np.zeros(nsamples // 2)
             for cc in range(nchains):
-                rho += acor1d(th[cc, :, n])
+                rho += acor1d(th[cc, :, n], zero_pad=zero_pad)
             rho /= nchains
         taus = 2 * np.cumsum(rho) - 1          # the -1: dfm/emcee issue 267
         window = auto_window(taus, c)

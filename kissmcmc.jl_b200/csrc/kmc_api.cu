@@ -781,8 +781,7 @@ int32_t kmc_emcee_create(kmc_density_t density, const double *theta0s, int64_t n
             const unsigned rounds = geometry(density->ops.run[r][1], kmc::kSmemThreads, kmc::kSmemCtas, density->ops.smem_per_walker, fits);
             s->use_smem = fits && rounds <= (unsigned)kmc::kRounds && s->smem_bytes <= (size_t)max_optin;
         }
-        s->use_bulk = !s->use_smem && opts->launch_mode == 0 && r == 0 && density->ops.run_bulk[0] &&
-                      !getenv("KMC_NO_BULK");
+        s->use_bulk = !s->use_smem && opts->launch_mode == 0 && r == 0 && density->ops.run_bulk[0];
         if (s->use_bulk) {  // 2 CTAs x 256 threads per SM, rows staged through shared memory
             const void *kb0 = density->ops.run_bulk[0], *kb1 = density->ops.run_bulk[1];
             cudaFuncSetAttribute(kb0, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)density->ops.bulk_smem);
@@ -961,10 +960,8 @@ int32_t kmc_emcee_run_half(kmc_sampler_t s, int64_t nhalfsteps) {
         q.nchunks = s->nchunks;
         q.cap = s->cap;
         q.lag = s->lag;
-        q.batch = 1;
-        q.age = 2;
-        if (const char *e = getenv("KMC_PUSH_BATCH")) q.batch = (unsigned)std::max(1, std::min(6, atoi(e)));  // profiling knobs
-        if (const char *e = getenv("KMC_PUSH_AGE")) q.age = (unsigned)std::max(1, std::min(3, atoi(e)));
+        q.batch = 1;  // measured on 8 B200s (profiles/r2_call13.log, r2_call14.log): notes posted singly, as soon as the
+        q.age = 2;    // newest message is two tasks old, beat every batched / later variant (flag latency gates the consumers)
         set_range(hbeg, hend);
         CU_TRY(cudaMemsetAsync(s->task_ctr, 0, 4 * sizeof(unsigned long long), s->stream));
         CU_TRY(cudaEventRecord(s->ev0, s->stream));

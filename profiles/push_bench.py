@@ -1,7 +1,7 @@
 """Sharded-ensemble throughput with the push exchange, one process driving all GPUs (kmc_emcee_create_multi).
-    python profiles/push_bench.py <log2 nwalkers> <iters> <devices, e.g. 0,1,2,3 | 0p> [chunk,cap,lag[,batch,age] ...]
-One JSON line per configuration (0 = library default; lag > 0 selects the ordered hand-out; batch / age are the
-profiling knobs KMC_PUSH_BATCH / KMC_PUSH_AGE).  A single device runs the unsharded sampler (the
+    python profiles/push_bench.py <log2 nwalkers> <iters> <devices, e.g. 0,1,2,3 | 0p> [chunk,cap,lag ...]
+One JSON line per configuration (0 = library default; lag > 0: ordered hand-out with that lag, -1: adaptive hand-out).
+(The batch / age columns of the round-2 logs were environment knobs of an experiment build; the library now fixes them.)  A single device runs the unsharded sampler (the
 1-GPU anchor); "0p" runs the push kernel with ONE rank (its task loop alone).  Device time = max over the devices'
 kernels (CUDA events on each launch stream)."""
 import json
@@ -27,11 +27,6 @@ ld = km.LogDensity("gaussian", d, params, device=devices[0])
 warm, G = 4, len(devices)
 S = nw // 2 // G
 for chunk, cap, lag, nbatch, age in cfgs:
-    for key, val in (("KMC_PUSH_BATCH", nbatch), ("KMC_PUSH_AGE", age)):
-        if val:
-            os.environ[key] = str(val)
-        else:
-            os.environ.pop(key, None)
     if G == 1:
         kw = dict(shard=(0, nw // 2), exchange=km.EXCHANGE_PUSH, push_chunk=chunk, push_lag=lag) if push1 else {}
         s = km.Sampler(ld, x0, iters + warm, 0, 10**6, 2.0, 7, device=devices[0], **kw)

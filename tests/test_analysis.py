@@ -104,3 +104,14 @@ def test_int_acorr_cuda_tensor_matches_numpy(km):
     t2, c2 = km.int_acorr(torch.from_numpy(x).cuda(), warn=False)
     np.testing.assert_allclose(t2, t0, rtol=1e-9)
     np.testing.assert_allclose(c2, c0, rtol=1e-9)
+
+
+def test_zero_padded_autocorrelation_is_the_linear_one(km):
+    """zero_pad=True (an extension; the reference's correlation is circular): equals the direct lag sums."""
+    x = _ar1(0.6, 1, 400, 9)[0]
+    xc = x - x.mean()
+    direct = np.array([np.dot(xc[:len(x) - k], xc[k:]) for k in range(len(x) // 2)])
+    np.testing.assert_allclose(km.acor1d(x, zero_pad=True), direct / direct[0], rtol=1e-10, atol=1e-12)
+    assert not np.allclose(km.acor1d(x), direct / direct[0], atol=1e-6)          # the default stays circular
+    t_lin, _ = km.int_acorr(_ar1(0.5, 8, 4000, 1), warn=False, zero_pad=True)
+    assert abs(t_lin[0] - 3.0) < 0.5                                               # AR(1): tau = (1 + phi) / (1 - phi)
