@@ -94,7 +94,7 @@ int32_t kmc_device_count(int32_t *count);
 int32_t kmc_trim(void);
 
 /* Log-density plugin registry: replaces the user closure `pdf` (src/samplers.jl:257,:209).
- *   "exponential"  README.md:15             params: none
+ *   "exponential"  README.md:15             params: none; any d <= 4096 (fused kernels for d in {1..6, 8, 10, 12, 16})
  *   "rosenbrock"   test/runtests.jl:68      params: [a, b, T] (reference: 1, 100, 20), d = 2
  *   "gaussian"     test/runtests.jl:53,61   params: [mu(d), A(d*d row-major), lognorm],
  *                                           logp = lognorm - 0.5*|A (x-mu)|^2

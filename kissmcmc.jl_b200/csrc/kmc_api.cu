@@ -103,7 +103,13 @@ namespace {
 
 bool find_ops(int kind, int d, Ops &o) {
     switch (kind) {
-        case kmc::KIND_EXPONENTIAL: return ops_exponential(d, o);
+        case kmc::KIND_EXPONENTIAL:
+            if (ops_exponential(d, o)) return true;
+            if (d > 4096) return false;
+            o = Ops();
+            o.batch = 3;  // any other dimension: batched half-step with a thread-per-point sum
+            o.nparams = 0;
+            return true;
         case kmc::KIND_GAUSSIAN:
             if (ops_gaussian(d, o)) return true;
             if (d > kmc::kWideMaxD) return false;
@@ -282,6 +288,10 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         kmc::gaussian_wide_logp_kernel<<<grid, kmc::kWideThreads, smem, st>>>(X, out, npts, d, dn.d_params, dn.d_At);
         return cudaGetLastError();
     }
+    if (dn.ops.batch == 3) {
+        kmc::exponential_wide_logp_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(X, out, npts, d);
+        return cudaGetLastError();
+    }
     if (dn.ops.batch == 2 && dn.tc_ok && dn.tc_on) {  // tcgen05 logits GEMM + fused softplus row sums
         cudaError_t e = batch_scratch_reserve(sc, dn, npts);
         if (e != cudaSuccess) return e;
@@ -399,10 +409,10 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
         h->params[3] = (T > 0x1p-100 && T < 0x1p100) ? 1.0 / params[2] : 0.0;
     }
     if (ops.batch) {  // batched plugins keep parameters (and data) in device memory
-        h->params.assign(params, params + nparams);
+        if (nparams) h->params.assign(params, params + nparams);
         cudaError_t e = cudaSetDevice(device);
-        if (e == cudaSuccess) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
-        if (e == cudaSuccess) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && nparams) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
+        if (e == cudaSuccess && nparams) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
         if (e == cudaSuccess && ops.batch == 1) {  // A^T padded to 128 rows for the FP64 kernel
             std::vector<double> At((size_t)d * 128, 0.0);
             for (int i = 0; i < d; ++i)

@@ -221,6 +221,23 @@ static __global__ void __launch_bounds__(kWideThreads, 1) gaussian_wide_logp_ker
     }
 }
 
+// ------------------------------------------------------------------ exponential, any d (README.md:15, d > 1: independent Exp(1))
+// The dimensions without a compiled fused kernel (d = 7, 9, 11, 13-15, d > 16) take the batched half-step with this
+// kernel: one thread per point, the components summed in index order with the oracle's operations -> bit-identical.
+static __global__ void __launch_bounds__(256) exponential_wide_logp_kernel(const double *__restrict__ X, double *__restrict__ out,
+                                                                          long long npts, int d) {
+    const long long pt = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (pt >= npts) return;
+    const double *x = X + pt * d;
+    double s = x[0];
+    bool neg = x[0] < 0.0;
+    for (int c = 1; c < d; ++c) {
+        neg = neg || (x[c] < 0.0);
+        s = dadd(s, x[c]);
+    }
+    out[pt] = neg ? -CUDART_INF : -s;
+}
+
 // ------------------------------------------------------------------ logistic regression, FP64
 // data: X[N][d] float32 row-major then y[N] float32 (0/1); params: [prior_sigma].
 //   logp(theta) = sum_n (y_n s_n - softplus(s_n)) - 0.5 |theta|^2 / sigma^2,  s_n = x_n . theta

@@ -310,3 +310,21 @@ def test_rosenbrock_analytic_moments_at_scale(km):
     # and inside the reference's own acceptance band around its quoted values
     assert np.all(np.abs(mean - [0.98, 10.3]) < 0.6 * np.array([3.1, 13.8]))
     assert np.all(np.abs(std - [3.1, 13.8]) < 0.6 * np.array([3.1, 13.8]))
+
+
+@pytest.mark.parametrize("d", [7, 9, 15, 20, 100])
+def test_exponential_any_dimension_matches_oracle(km, orc, d):
+    """d without a compiled fused kernel (7, 9, 11, 13-15, > 16) runs the batched half-step with a thread-per-point sum in
+    the oracle's order: eval and a seeded run are bit-identical to the oracle."""
+    ld, od = km.exponential(d), orc.Density("exponential", d, [])
+    assert ld.info("batched") == 3.0
+    rng = np.random.default_rng(d)
+    pts = rng.standard_normal((500, d)) + 1.0
+    assert np.array_equal(ld.eval(pts), od.eval(pts))
+    nw = 2 * (d + 3)
+    x0 = np.abs(1.0 + 0.1 * rng.standard_normal((nw, d)))
+    want = orc.emcee(od, x0, 30, 10, 3, 2.0, seed=5, nthreads=2)
+    for launch_mode in (0, 1):
+        r = _run_gpu(km, ld, x0, 30, 10, 3, 2.0, seed=5, launch_mode=launch_mode)
+        assert np.array_equal(r["chain_x"], want["chain_x"]) and np.array_equal(r["chain_lp"], want["chain_lp"])
+        assert np.array_equal(r["accept_ratio"], want["accept_ratio"])
