@@ -328,3 +328,19 @@ def test_exponential_any_dimension_matches_oracle(km, orc, d):
         r = _run_gpu(km, ld, x0, 30, 10, 3, 2.0, seed=5, launch_mode=launch_mode)
         assert np.array_equal(r["chain_x"], want["chain_x"]) and np.array_equal(r["chain_lp"], want["chain_lp"])
         assert np.array_equal(r["accept_ratio"], want["accept_ratio"])
+
+
+def test_very_long_chain_of_few_walkers_copies_out(km, orc):
+    """Few walkers, > 2.09 M stored samples each (gridDim.y of one transpose launch would overflow): results come back
+    and equal the oracle's at both ends of the chain."""
+    ld, od = km.exponential(), orc.Density("exponential", 1, [])
+    x0 = np.array([[0.5], [0.7], [0.9], [1.1]])
+    nitw = 65535 * 32 + 1000
+    s = km.Sampler(ld, x0, nitw, 0, 1, 2.0, seed=3)
+    s.run(-1)
+    th, lp, ar = s.results()
+    s.close()
+    assert th.shape == (4, nitw, 1) and np.all(np.isfinite(lp)) and np.all(th >= 0)
+    want = orc.emcee(od, x0, 2000, 0, 1, 2.0, seed=3, nthreads=1)
+    assert np.array_equal(th[:, :2000], want["chain_x"]) and np.array_equal(lp[:, :2000], want["chain_lp"])
+    assert np.array_equal(lp[:, -1], -th[:, -1, 0]) and 0.3 < ar.mean() < 0.95

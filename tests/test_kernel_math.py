@@ -138,3 +138,23 @@ def test_balanced_tiling_of_the_fused_gaussian_kernels_covers_every_walker_once(
                 covered += max(0, min(tr, W - w0))
         assert covered == W, (W, grid, waves, tr, ntiles)
         assert (ntiles - 1) * tr < W <= ntiles * tr
+
+
+def test_chain_transpose_launch_geometry_covers_long_chains():
+    """kmc_emcee_copy_results transposes the sample-major chain in launches of at most kTransposeMaxSamples samples
+    (gridDim.y <= 65535 blocks of 32 samples): every sample exactly once, for chains far beyond 2.09 M samples."""
+    src = (CSRC / "kmc_kernels.cuh").read_text()
+    m = re.search(r"kTransposeMaxSamples = (\d+)LL \* (\d+);", src)
+    max_samples = int(m.group(1)) * int(m.group(2))
+    assert max_samples == 65535 * 32
+    api = (CSRC / "kmc_api.cu").read_text()
+    assert api.count("s0 += kmc::kTransposeMaxSamples") == 2          # thetas and logp both loop over sample chunks
+    for ns in (1, 31, 32, max_samples - 1, max_samples, max_samples + 1, 5_000_000, 3 * max_samples + 7):
+        covered = 0
+        for s0 in range(0, ns, max_samples):
+            sc = min(max_samples, ns - s0)
+            grid_y = (sc + 31) // 32
+            assert 1 <= grid_y <= 65535
+            assert grid_y * 32 >= sc                                    # the launch reaches the chunk's last sample
+            covered += sc
+        assert covered == ns
