@@ -6,6 +6,9 @@
 // operation goes through the __d*_rn intrinsics, which nvcc never fuses.
 #pragma once
 #include <cstdint>
+#ifndef KMC_U48_BITS
+#define KMC_U48_BITS 0
+#endif
 #include <cuda_runtime.h>
 
 namespace kmc {
@@ -107,8 +110,15 @@ __device__ __forceinline__ void draw(const PhiloxKeys &ks, uint32_t walker, uint
     partner_local = hi;
     const uint64_t bz = ((uint64_t)r.r1 << 16) | (r.r2 >> 16);
     const uint64_t ba = ((uint64_t)(r.r2 & 0xFFFFu) << 32) | r.r3;
+#if KMC_U48_BITS
+    // the same values without the two U64 -> F64 conversions (XU pipe): 1 + b*2^-48 assembled in the mantissa, then an
+    // exact subtraction of 1
+    uz = __dadd_rn(__longlong_as_double((long long)(0x3FF0000000000000ULL | (bz << 4))), -1.0);
+    uacc = __dadd_rn(__longlong_as_double((long long)(0x3FF0000000000000ULL | (ba << 4))), -1.0);
+#else
     uz = (double)bz * 0x1p-48;    // exact: 48-bit integer times a power of two
     uacc = (double)ba * 0x1p-48;
+#endif
 }
 
 // ------------------------------------------------------------------ log-density plugins

@@ -17,6 +17,7 @@
 // With a range of one half-step the kernel degenerates to "one launch per half-step".
 #pragma once
 #include <math_constants.h>
+#include <type_traits>
 
 #include "kmc_device.cuh"
 
@@ -89,6 +90,22 @@ __device__ __forceinline__ void barrier_wait(const unsigned long long *ctr, unsi
         }
     } while (v < target);
     asm volatile("fence.acq_rel.gpu;" ::: "memory");
+}
+
+// The shared-memory kernel's wait: acquire loads (LDG.STRONG.GPU + CCTL.IVALL) instead of relaxed loads + fence.acq_rel.gpu
+// (MEMBAR.ALL.GPU + ERRBAR): measured 0.4 us per half-step of that kernel.  Every poll invalidates the SM's L1, which that
+// kernel never uses for global data (partner rows are .cg loads).
+__device__ __forceinline__ void barrier_wait_acquire(const unsigned long long *ctr, unsigned long long target) {
+    unsigned long long v;
+    long long t0 = 0;
+    unsigned spins = 0;
+    do {
+        asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(ctr) : "memory");
+        if (v < target && (++spins & 0xFFFu) == 0) {  // watchdog (~20 s)
+            if (t0 == 0) t0 = clock64();
+            else if (clock64() - t0 > 40000000000LL) __trap();
+        }
+    } while (v < target);
 }
 
 // ------------------------------------------------------------------ accept test
@@ -567,24 +584,40 @@ static __global__ void __launch_bounds__(kBulkThreads, KMC_BULK_CTAS) emcee_bulk
 // ------------------------------------------------------------------ shared-memory-resident kernel
 // x / logp / accept counters of the CTA's walkers live in shared memory for the whole launch;
 // global x is only written on accept (so partners can gather it) and logp / counters are
-// written back once at the end.  Geometry (threads x rounds x CTAs per SM) was swept on a B200 for
-// the 2^20-walker config: 384x5x2 7.36 us per half-step, 448x4x2 7.54, 512x4x2 7.52, 320x6x2 7.48,
-// 896x4x1 8.01, 640x6x1 8.12, 256x7x3 10.4.  Every thread owns at most kRounds walker positions of each
+// written back once at the end.  Every thread owns at most kRounds walker positions of each
 // half: slot(half b, round q) = b*per_cta + q*blockDim + tid.  Layout (L = 2*per_cta slots),
 // component-major so that a warp's accesses are conflict-free:
 //   double xs[D][L]; double lps[L]; unsigned naccs[L];
-// Per half-step: the draws (Philox) of all rounds were made in the previous barrier's shadow;
-// partner rows are prefetched two rounds ahead.
+// Per half-step: the draws (Philox) of the first kSmemSplit rounds are made in the grid barrier's shadow, the others
+// right after the first partner gathers are issued (under their L2 latency); partner rows are prefetched two rounds
+// ahead.  Thread 0 arrives (release), the last warp polls (acquire loads).
+// Geometry and split were swept on a B200 for the 2^20-walker config (us per half-step, profiles/r2_k1_variants_*.log):
+// round 1 form (all draws in the shadow) 384x5x2 7.30; split 2: 384x5x2 6.85, 320x6x2 6.73, 256x7x2 6.65 (1771 positions
+// per CTA = 6.92 x 256: every round full), 224x8x2 7.07, 192x10x2 7.67, 128x14x2 9.75, 448x4x2 7.70 (72-register cap),
+// 256x5x3 9.64, 512x7x1 6.75; 256x7x2 with split 1 / 3 / 4 / 5 / 7: 6.89 / 6.48 / 6.52 / 6.69 / 7.57; + last warp
+// polls: split 3 / 4 / 5 = 6.40 / 6.37 / 6.53; + acquire polls instead of relaxed polls and a fence: split 4 / 5 / 6 =
+// 6.02 / 6.14 / 6.32.  Measured without gain: 3 partner rows in flight, two polls in flight, next round's own row
+// preloaded, two rounds' proposals and log-densities interleaved per thread, per-warp arrivals (12x the atomics: 7.66),
+// draws made inside the round loop (7.45), bit-assembled uniforms instead of I2F.F64.U64.
 #ifndef KMC_SMEM_ROUNDS
-#define KMC_SMEM_ROUNDS 5
+#define KMC_SMEM_ROUNDS 7
 #endif
 #ifndef KMC_SMEM_THREADS
-#define KMC_SMEM_THREADS 384
+#define KMC_SMEM_THREADS 256
 #endif
 #ifndef KMC_SMEM_CTAS
 #define KMC_SMEM_CTAS 2
 #endif
+#ifndef KMC_SMEM_SPLIT
+#define KMC_SMEM_SPLIT 4
+#endif
 constexpr int kRounds = KMC_SMEM_ROUNDS;
+constexpr int kSmemSplit = KMC_SMEM_SPLIT;  // draws of rounds [0, split) in the barrier's shadow, the rest after it (>= 2)
+#ifndef KMC_SMEM_AHEAD
+#define KMC_SMEM_AHEAD 2
+#endif
+constexpr int kAhead = KMC_SMEM_AHEAD;  // partner rows in flight per thread
+static_assert(kSmemSplit >= kAhead && kSmemSplit <= kRounds, "the first partner gathers need their draws");
 constexpr int kSmemThreads = KMC_SMEM_THREADS;
 constexpr int kSmemCtas = KMC_SMEM_CTAS;  // CTAs per SM the kernel is compiled and launched for
 
@@ -640,9 +673,9 @@ static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_ker
     // a thread only ever touches the slots it staged itself: no sync needed
 
     DrawRec dr[kRounds];
-    auto make_draws = [&](long long h) {
+    auto make_draws = [&](long long h, auto lo, auto hi) {  // rounds [lo, hi) of half-step h
 #pragma unroll
-        for (int q = 0; q < kRounds; ++q)
+        for (int q = decltype(lo)::value; q < decltype(hi)::value; ++q)
             if (q < nv) {
                 unsigned j;
                 double z, u;
@@ -652,7 +685,10 @@ static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_ker
                 dr[q].q = filter_q<REPLAY>(p, z, u);
             }
     };
-    make_draws(p.h0);
+    using SplitLo = std::integral_constant<int, 0>;
+    using SplitMid = std::integral_constant<int, kSmemSplit>;
+    using SplitHi = std::integral_constant<int, kRounds>;
+    make_draws(p.h0, SplitLo{}, SplitMid{});
 
     // launch-local 32-bit bookkeeping of the reference's n (:245), rem(n, nthin) and the sample index
     const unsigned nh = (unsigned)(p.h1 - p.h0);
@@ -667,9 +703,11 @@ static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_ker
         const unsigned hslot = batch ? p.per_cta : 0u;            // first slot of the active half
         const size_t hrow = batch ? (size_t)p.nhalf : (size_t)0;  // first global row of the active half (:247)
 
-        double xj[2][D];
-        if (0 < nv) load_row_cg<D>(p.x + (size_t)dr[0].j * D, xj[0]);
-        if (1 < nv) load_row_cg<D>(p.x + (size_t)dr[1].j * D, xj[1]);
+        double xj[kAhead][D];
+#pragma unroll
+        for (int q = 0; q < kAhead; ++q)
+            if (q < nv) load_row_cg<D>(p.x + (size_t)dr[q].j * D, xj[q]);
+        make_draws(h, SplitMid{}, SplitHi{});  // the later rounds' draws, under the first gathers' L2 latency
 #pragma unroll
         for (int q = 0; q < kRounds; ++q) {
             if (q >= nv) break;
@@ -681,9 +719,9 @@ static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_ker
             const double lpk = lds_f64(sbase + 8u * (D * L + sl));
             const double z = dr[q].z;
 #pragma unroll
-            for (int c = 0; c < D; ++c) y[c] = dadd(xj[q & 1][c], dmul(z, dsub(xk[c], xj[q & 1][c])));  // :255
-            if (q + 2 < kRounds && q + 2 < nv)  // partner row two rounds ahead, before this round's stores
-                load_row_cg<D>(p.x + (size_t)dr[(q + 2) % kRounds].j * D, xj[q & 1]);
+            for (int c = 0; c < D; ++c) y[c] = dadd(xj[q % kAhead][c], dmul(z, dsub(xk[c], xj[q % kAhead][c])));  // :255
+            if (q + kAhead < kRounds && q + kAhead < nv)  // partner row kAhead rounds ahead, before this round's stores
+                load_row_cg<D>(p.x + (size_t)dr[(q + kAhead) % kRounds].j * D, xj[q % kAhead]);
             const double p1 = dn.logpdf(y);                                        // :257
             const double tt = (p1 - lpk) + (double)dr[q].q * 0.6931471805599453;  // :260
             bool acc;
@@ -713,9 +751,10 @@ static __global__ void __launch_bounds__(kSmemThreads, kSmemCtas) emcee_smem_ker
             target += gridDim.x;
             __syncthreads();
             if (gridDim.x > 1 && threadIdx.x == 0) barrier_arrive(p.barrier);
-            make_draws(h + 1);  // in the barrier's shadow: independent of the other CTAs
+            make_draws(h + 1, SplitLo{}, SplitMid{});  // in the barrier's shadow: independent of the other CTAs
             if (gridDim.x > 1) {
-                if (threadIdx.x == 0) barrier_wait(p.barrier, target);
+                // the LAST warp polls: thread 0's warp is still behind its release (a membar over the CTA's row stores)
+                if (threadIdx.x == blockDim.x - 32) barrier_wait_acquire(p.barrier, target);
                 __syncthreads();
             }
         }
