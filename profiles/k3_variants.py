@@ -15,6 +15,7 @@ wl = dict(bench.WORKLOADS["logistic32d"])
 params, x0 = bench.make_inputs(wl, 1)
 ld = km.LogDensity(wl["plugin"], wl["d"], params, data=wl.get("_data"))
 pts = x0[:512]
+ld.set_option("tensor_cores", 1)      # opt-in since round 2
 got = ld.eval(pts)
 ld.set_option("tensor_cores", 0)
 want = ld.eval(pts)
