@@ -97,7 +97,9 @@ int32_t kmc_trim(void);
  *   "exponential"  README.md:15             params: none; any d <= 4096 (fused kernels for d in {1..6, 8, 10, 12, 16})
  *   "rosenbrock"   test/runtests.jl:68      params: [a, b, T] (reference: 1, 100, 20), d = 2
  *   "gaussian"     test/runtests.jl:53,61   params: [mu(d), A(d*d row-major), lognorm],
- *                                           logp = lognorm - 0.5*|A (x-mu)|^2
+ *                                           logp = lognorm - 0.5*|A (x-mu)|^2; any d <= 4096 (fused FP64 kernels for
+ *                                           d in {1..6, 8, 10, 12, 16}; batched FP64 otherwise, the matrix in shared
+ *                                           memory up to d = 128 and in L2 beyond)
  *   "lognormal"    test/runtests.jl:56      params: [mu, sigma, log(sigma)+0.5*log(2pi)], d = 1
  *   "logistic"     BASELINE.json config 4   params: [prior_sigma]; data: float32 X[N][d] then y[N]
  * `data` may be NULL.  params/data are copied; the caller may free them on return. */
@@ -107,7 +109,7 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
 int32_t kmc_density_destroy(kmc_density_t h);
 /* Options: "tensor_cores" = 0/1.  Every plugin is exact FP64 by default.  1 opts in to the tcgen05 kernels, which are
  * APPROXIMATE with a stated tolerance: the dense Gaussian with 16 < d <= 128 (|logp - logp_fp64| <= 1e-5 (1 + |y|^2))
- * and logistic regression with d = 32 and bf16-representable data (log-density DIFFERENCES between nearby points --
+ * and logistic regression with d <= 64 and bf16-representable data (log-density DIFFERENCES between nearby points --
  * what the accept test sees -- within 2e-3 at N = 10^6; the value itself carries a common offset of up to ~1e-7 N
  * that cancels in every accept test but is present in the stored log-densities).  Returns KMC_ERR_UNSUPPORTED if the
  * density has no tensor-core path.

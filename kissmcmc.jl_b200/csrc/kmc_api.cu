@@ -112,9 +112,9 @@ bool find_ops(int kind, int d, Ops &o) {
             return true;
         case kmc::KIND_GAUSSIAN:
             if (ops_gaussian(d, o)) return true;
-            if (d > kmc::kWideMaxD) return false;
+            if (d > kmc::kHugeMaxD) return false;
             o = Ops();
-            o.batch = 1;  // dense contraction over the active half
+            o.batch = 1;  // dense contraction over the active half (d > 128: FP64 from L2, no tensor-core path)
             o.nparams = d + d * d + 1;
             return true;
         case kmc::KIND_LOGISTIC:
@@ -277,6 +277,19 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
                                                                                     wpad, d);
         return launch_gauss_tc(dn, sc, npts, out, st);
     }
+    if (dn.ops.batch == 1 && d > kmc::kWideMaxD) {
+        const int dpad = (d + 127) / 128 * 128;
+        const size_t per_warp = sizeof(double) * (size_t)d * kmc::kWidePts;
+        const int wpb = (int)std::max<size_t>(1, std::min<size_t>(kmc::kWideThreads / 32, (size_t)(200 * 1024) / per_warp));
+        const size_t smem = per_warp * wpb;
+        cudaError_t e = cudaFuncSetAttribute(kmc::gaussian_huge_logp_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        const long long ngroups = (npts + kmc::kWidePts - 1) / kmc::kWidePts;
+        const unsigned grid = (unsigned)std::min<long long>((ngroups + wpb - 1) / wpb, 2LL * dn.nsm);
+        kmc::gaussian_huge_logp_kernel<<<grid, wpb * 32, smem, st>>>(X, out, npts, d, dpad, dn.d_params, dn.d_At);
+        return cudaGetLastError();
+    }
     if (dn.ops.batch == 1) {
         const size_t smem = sizeof(double) * ((size_t)d * 128 + (size_t)(kmc::kWideThreads / 32) * d * kmc::kWidePts);
         cudaError_t e = cudaFuncSetAttribute(kmc::gaussian_wide_logp_kernel,
@@ -413,17 +426,20 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
         cudaError_t e = cudaSetDevice(device);
         if (e == cudaSuccess && nparams) e = dev_alloc(&h->d_params, sizeof(double) * nparams, device);
         if (e == cudaSuccess && nparams) e = cudaMemcpy(h->d_params, params, sizeof(double) * nparams, cudaMemcpyHostToDevice);
-        if (e == cudaSuccess && ops.batch == 1) {  // A^T padded to 128 rows for the FP64 kernel
-            std::vector<double> At((size_t)d * 128, 0.0);
+        if (e == cudaSuccess && ops.batch == 1) {  // A^T padded to a multiple of 128 rows for the FP64 kernels
+            const size_t dpad = (size_t)(d + 127) / 128 * 128;
+            std::vector<double> At((size_t)d * dpad, 0.0);
             for (int i = 0; i < d; ++i)
-                for (int j = 0; j < d; ++j) At[(size_t)j * 128 + i] = params[d + (size_t)i * d + j];
+                for (int j = 0; j < d; ++j) At[(size_t)j * dpad + i] = params[d + (size_t)i * d + j];
             e = dev_alloc(&h->d_At, sizeof(double) * At.size(), device);
             if (e == cudaSuccess) e = cudaMemcpy(h->d_At, At.data(), sizeof(double) * At.size(), cudaMemcpyHostToDevice);
         }
-        if (e == cudaSuccess && ops.batch == 1) {  // matrix pieces for the tcgen05 Mahalanobis GEMM
+        if (e == cudaSuccess && ops.batch == 1) {
             int nsm = 0;
             cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
             h->nsm = nsm > 0 ? nsm : 148;
+        }
+        if (e == cudaSuccess && ops.batch == 1 && d <= kmc::kWideMaxD) {  // matrix pieces for the tcgen05 Mahalanobis GEMM
             e = dev_alloc(&h->d_Abf, sizeof(__nv_bfloat16) * kmc::tc::PIECES * kmc::tc::GN * kmc::tc::GK, device);
             if (e == cudaSuccess) {
                 const long long ne = (long long)kmc::tc::GN * kmc::tc::GK;

@@ -221,6 +221,65 @@ static __global__ void __launch_bounds__(kWideThreads, 1) gaussian_wide_logp_ker
     }
 }
 
+// Dense Gaussian for 128 < d <= kHugeMaxD: the same register tile and accumulation order, in blocks of 128 rows, with the
+// transposed matrix At_g[j][dpad] (dpad = d rounded up to 128, zero rows past d) read from L2 instead of shared memory
+// (8 d^2 bytes no longer fit).  The reference takes any d (a user closure, src/samplers.jl:257); no tensor-core path here.
+constexpr int kHugeMaxD = 4096;
+static __global__ void __launch_bounds__(kWideThreads, 1) gaussian_huge_logp_kernel(const double *__restrict__ X,
+                                                                                   double *__restrict__ out, long long npts,
+                                                                                   int d, int dpad,
+                                                                                   const double *__restrict__ prm,
+                                                                                   const double *__restrict__ At_g) {
+    extern __shared__ double sm[];  // [warps][d][kWidePts]: the centred points of each warp's group
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const double lognorm = prm[d + (size_t)d * d];
+    double *c = sm + (size_t)wib * d * kWidePts;
+    const long long ngroups = (npts + kWidePts - 1) / kWidePts;
+    for (long long g = (long long)blockIdx.x * nwarp + wib; g < ngroups; g += (long long)gridDim.x * nwarp) {
+        const long long pt0 = g * kWidePts;
+#pragma unroll
+        for (int w = 0; w < kWidePts; ++w) {
+            const long long pt = pt0 + w;
+            for (int j = lane; j < d; j += 32) c[j * kWidePts + w] = pt < npts ? X[pt * d + j] - prm[j] : 0.0;
+        }
+        __syncwarp();
+        double ss[kWidePts];
+#pragma unroll
+        for (int w = 0; w < kWidePts; ++w) ss[w] = 0.0;
+        for (int rb = 0; rb < dpad; rb += 128) {  // rows rb + lane + 32 r of y
+            double acc[kWidePts][4];
+#pragma unroll
+            for (int w = 0; w < kWidePts; ++w)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) acc[w][r] = 0.0;
+            const double *col = At_g + rb + lane;
+            for (int j = 0; j < d; ++j) {
+                const double2 c01 = *reinterpret_cast<const double2 *>(c + j * kWidePts);
+                const double2 c23 = *reinterpret_cast<const double2 *>(c + j * kWidePts + 2);
+                const double cj[4] = {c01.x, c01.y, c23.x, c23.y};
+                const double *row = col + (size_t)j * dpad;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const double a = __ldg(row + 32 * r);
+#pragma unroll
+                    for (int w = 0; w < kWidePts; ++w) acc[w][r] = fma(a, cj[w], acc[w][r]);
+                }
+            }
+#pragma unroll
+            for (int w = 0; w < kWidePts; ++w)
+#pragma unroll
+                for (int r = 0; r < 4; ++r) ss[w] = fma(acc[w][r], acc[w][r], ss[w]);
+        }
+#pragma unroll
+        for (int w = 0; w < kWidePts; ++w) {
+            double s = ss[w];
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0 && pt0 + w < npts) out[pt0 + w] = lognorm - 0.5 * s;
+        }
+        __syncwarp();
+    }
+}
+
 // ------------------------------------------------------------------ exponential, any d (README.md:15, d > 1: independent Exp(1))
 // The dimensions without a compiled fused kernel (d = 7, 9, 11, 13-15, d > 16) take the batched half-step with this
 // kernel: one thread per point, the components summed in index order with the oracle's operations -> bit-identical.

@@ -27,13 +27,25 @@ def test_wide_gaussian_eval(km, orc, d):
     np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-12, atol=0)
 
 
-def test_wide_gaussian_d129_unsupported(km):
+@pytest.mark.parametrize("d,npts", [(129, 777), (200, 333), (512, 130), (1000, 9)])
+def test_gaussian_beyond_128_dimensions(km, orc, d, npts):
+    """128 < d <= 4096: the FP64 kernel with the matrix in L2 (the reference takes any d: a closure, src/samplers.jl:257).
+    Same accumulation as the d <= 128 kernel -> the same stated tolerance against the oracle; no tensor-core path."""
+    ld, od = _gauss(km, orc, d)
+    pts = np.random.default_rng(1).standard_normal((npts, d)) * 2
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-12, atol=0)
+    assert ld.info("tensor_cores_available") == 0
+    with pytest.raises(km.KmcError):
+        ld.set_option("tensor_cores", 1)
+
+
+def test_gaussian_dimension_limit(km):
     with pytest.raises(km.KmcError) as e:
-        km.LogDensity("gaussian", 129, np.zeros(129 + 129 * 129 + 1))
+        km.LogDensity("gaussian", 4097, np.zeros(4097 + 4097 * 4097 + 1))
     assert e.value.code == 3
 
 
-@pytest.mark.parametrize("d,nw,nitw,nbw,nthin", [(100, 512, 12, 4, 2), (40, 200, 9, 0, 1)])
+@pytest.mark.parametrize("d,nw,nitw,nbw,nthin", [(100, 512, 12, 4, 2), (40, 200, 9, 0, 1), (160, 324, 8, 2, 2)])
 def test_wide_gaussian_replay_parity(km, orc, d, nw, nitw, nbw, nthin):
     ld, od = _gauss(km, orc, d)
     x0 = cases.ball(np.zeros(d), 0.5, nw, 5)
