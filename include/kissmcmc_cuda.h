@@ -101,7 +101,7 @@ int32_t kmc_trim(void);
  *                                           d in {1..6, 8, 10, 12, 16}; batched FP64 otherwise, the matrix in shared
  *                                           memory up to d = 128 and in L2 beyond)
  *   "lognormal"    test/runtests.jl:56      params: [mu, sigma, log(sigma)+0.5*log(2pi)], d = 1
- *   "logistic"     BASELINE.json config 4   params: [prior_sigma]; data: float32 X[N][d] then y[N]
+ *   "logistic"     BASELINE.json config 4   params: [prior_sigma]; data: float32 X[N][d] then y[N]; any d <= 512
  * `data` may be NULL.  params/data are copied; the caller may free them on return. */
 int32_t kmc_density_create(const char *name, int32_t d, const double *params, int64_t nparams,
                            const void *data, int64_t data_bytes, int32_t device,

@@ -115,7 +115,7 @@ def logistic(X, y, prior_sigma: float = 10.0, device: int = 0, tensor_cores: boo
     """Bayesian logistic regression (BASELINE.json configs[3]): X [N, d], y [N] in {0, 1}, prior N(0, sigma^2 I).
     logp(theta) = sum_n (y_n s_n - softplus(s_n)) - |theta|^2 / (2 sigma^2),  s_n = x_n . theta.
 
-    Exact FP64 by default.  tensor_cores=True opts in to the tcgen05 kernel (needs d == 32 and every X value
+    Exact FP64 by default.  Any d <= 512.  tensor_cores=True opts in to the tcgen05 kernel (needs d <= 64 and every X value
     bf16-representable, else KmcError): theta split into three bf16 pieces, FP32 accumulation, FP32 softplus.
     It is APPROXIMATE: log-density differences between nearby points (what the accept test sees) agree with FP64 to
     2e-3 at N = 10^6 (6e-4 rms); the value itself -- the stored `logdensities` and the initial p0s -- carries a common

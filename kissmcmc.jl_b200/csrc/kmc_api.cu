@@ -101,6 +101,8 @@ void dev_free(void *p) {
 
 namespace {
 
+constexpr int kLogisticMaxD = 512;
+
 bool find_ops(int kind, int d, Ops &o) {
     switch (kind) {
         case kmc::KIND_EXPONENTIAL:
@@ -118,7 +120,7 @@ bool find_ops(int kind, int d, Ops &o) {
             o.nparams = d + d * d + 1;
             return true;
         case kmc::KIND_LOGISTIC:
-            if (d > 64) return false;
+            if (d > kLogisticMaxD) return false;  // 32 points' theta in shared memory; tcgen05 path up to d = 64
             o = Ops();
             o.batch = 2;
             o.nparams = 1;
@@ -339,6 +341,10 @@ cudaError_t launch_batch_logp(const kmc_density_s &dn, const double *X, long lon
         const long long rows = (dn.ndata + kLogitChunks - 1) / kLogitChunks;
         const size_t smem = sizeof(double) * ((size_t)kmc::kLogitTile * d + 8 * kmc::kLogitTile);
         const dim3 grid((unsigned)((npts + kmc::kLogitTile - 1) / kmc::kLogitTile), kLogitChunks);
+        if (smem > 48 * 1024) {
+            e = cudaFuncSetAttribute(kmc::logistic_logp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
         kmc::logistic_logp_kernel<<<grid, 256, smem, st>>>(X, sc.part, npts, d, dn.d_X, dn.d_y, dn.ndata, rows);
         const double sg = dn.params[0];
         kmc::logistic_finish_kernel<<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(X, sc.part, out, npts, d,
@@ -469,14 +475,16 @@ int32_t kmc_density_create(const char *name, int32_t d, const double *params, in
             if (e == cudaSuccess)
                 e = cudaMemcpy(h->d_y, (const float *)data + N * d, sizeof(float) * N, cudaMemcpyHostToDevice);
             // tcgen05 path: d <= 64 (zero-padded to K = 32 or 64) and every X value exactly representable in bf16
+            {
+                int nsm = 0;
+                cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+                h->nsm = nsm > 0 ? nsm : 148;
+            }
             if (e == cudaSuccess && d <= 64) {
                 h->kp = d <= 32 ? 32 : 64;
                 const uint32_t *xb = reinterpret_cast<const uint32_t *>(data);
                 bool exact = true;
                 for (long long i = 0; i < N * d && exact; ++i) exact = (xb[i] & 0xFFFFu) == 0;
-                int nsm = 0;
-                cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
-                h->nsm = nsm > 0 ? nsm : 148;
                 if (exact) {
                     // X^T (y - 1/2) in FP64: the y_n s_n term and the s_n/2 term of softplus(s) = s/2 + |s|/2 +
                     // log1p(e^-|s|) together are then an exact d-dot (logistic_tc_finish_kernel)

@@ -162,10 +162,25 @@ def test_logistic_tensor_core_not_used_when_ineligible(km):
     assert e.value.code == 3
     with pytest.raises(km.KmcError):
         km.logistic(X2, y, tensor_cores=True)
-    X65, y65, _ = cases.logistic_problem(N=500, d=65, seed=1)   # d > 64: no kernel at all
+    X65, y65, _ = cases.logistic_problem(N=500, d=65, seed=1)   # d > 64: FP64 kernel only
+    ld65 = km.logistic(X65, y65)
+    assert ld65.info("tensor_cores_available") == 0.0
+    with pytest.raises(km.KmcError):
+        ld65.set_option("tensor_cores", 1)
+    X513, y513, _ = cases.logistic_problem(N=50, d=513, seed=1)  # d > 512: no kernel at all
     with pytest.raises(km.KmcError) as e:
-        km.logistic(X65, y65)
+        km.logistic(X513, y513)
     assert e.value.code == 3
+
+
+@pytest.mark.parametrize("d,N", [(65, 3000), (200, 1500), (512, 700)])
+def test_logistic_fp64_beyond_64_dimensions(km, orc, d, N):
+    """64 < d <= 512 on the exact FP64 kernel (more than 48 KB of shared memory for the 32 points' theta beyond d = 191)."""
+    X, y, tstar = cases.logistic_problem(N=N, d=d, seed=4)
+    ld = km.logistic(X, y, prior_sigma=3.0)
+    od = orc.Density("logistic", d, [3.0], data=np.concatenate([X.ravel(), y]))
+    pts = tstar + cases.ball(np.zeros(d), 0.05, 70, 2)
+    np.testing.assert_allclose(ld.eval(pts), od.eval(pts), rtol=1e-10)
 
 
 def test_logistic_tensor_core_sampling(km):
