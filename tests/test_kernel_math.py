@@ -158,3 +158,40 @@ def test_chain_transpose_launch_geometry_covers_long_chains():
             assert grid_y * 32 >= sc                                    # the launch reaches the chunk's last sample
             covered += sc
         assert covered == ns
+
+
+def _smem_geometry(scnt, nsm=148):
+    """Host mirror of the persistent-launch geometry of kmc_emcee_create (kmc_api.cu, `geometry` lambda) for the
+    shared-memory kernel, with the constants read from kmc_kernels.cuh."""
+    src = (CSRC / "kmc_kernels.cuh").read_text()
+    threads = int(re.search(r"#define KMC_SMEM_THREADS (\d+)", src).group(1))
+    rounds_max = int(re.search(r"#define KMC_SMEM_ROUNDS (\d+)", src).group(1))
+    ctas = int(re.search(r"#define KMC_SMEM_CTAS (\d+)", src).group(1))
+    split = int(re.search(r"#define KMC_SMEM_SPLIT (\d+)", src).group(1))
+    ahead = int(re.search(r"#define KMC_SMEM_AHEAD (\d+)", src).group(1))
+    grid = min(-(-scnt // threads), ctas * nsm)
+    per_cta = -(-scnt // grid)
+    grid = -(-scnt // per_cta)
+    rounds = -(-per_cta // threads)
+    block = min(threads, -(-(-(-per_cta // rounds)) // 32) * 32)
+    return dict(threads=threads, rounds_max=rounds_max, split=split, ahead=ahead, grid=grid, per_cta=per_cta,
+                rounds=rounds, block=block)
+
+
+def test_shared_memory_kernel_geometry_of_the_bench_config():
+    """BASELINE.json configs[1] (2^20 walkers, 2^19 per half-step) on 148 SMs: 296 CTAs x 256 threads, 7 rounds, and every
+    round full -- the reason for 256 x 7 (the 384 x 5 of round 1 ran its fifth round 61 % full)."""
+    g = _smem_geometry(1 << 19)
+    assert (g["grid"], g["block"], g["rounds"], g["per_cta"]) == (296, 256, 7, 1772)
+    assert g["rounds"] <= g["rounds_max"]
+    assert g["per_cta"] / (g["rounds"] * g["block"]) > 0.98                 # rounds 98.9 % full
+    assert 2 * g["per_cta"] * 28 <= 113 * 1024                              # x, logp, counter of both halves: 2 CTAs per SM
+    assert g["ahead"] <= g["split"] <= g["rounds_max"]                      # the first gathers' draws are made in the shadow
+    # every owned position is covered exactly once by (round, thread)
+    owned = [q * g["block"] + t for q in range(g["rounds"]) for t in range(g["block"]) if q * g["block"] + t < g["per_cta"]]
+    assert owned == list(range(g["per_cta"]))
+    # the README example (100 walkers) and a ragged size: one CTA / a last warp that exists (it is the polling warp)
+    assert _smem_geometry(50)["grid"] == 1 and _smem_geometry(50)["block"] == 64
+    for scnt in (33, 257, 1000, 12345, 300000):
+        gg = _smem_geometry(scnt)
+        assert gg["block"] % 32 == 0 and gg["block"] >= 32 and gg["rounds"] * gg["block"] >= gg["per_cta"]
