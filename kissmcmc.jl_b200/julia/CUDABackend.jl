@@ -101,7 +101,7 @@ lognormal(mu=0.0, sigma=1.0; device=0) =
     logistic(X, y; prior_sigma=10.0, device=0, tensor_cores=false)
 
 Bayesian logistic regression (BASELINE.json configs[3]): `X` is N x d, `y` in {0,1}, prior N(0, sigma^2 I).
-Exact FP64 by default; `tensor_cores=true` opts in to the tcgen05 kernel (d == 32 and bf16-representable X), which is
+Exact FP64 by default; `tensor_cores=true` opts in to the tcgen05 kernel (d <= 64 and bf16-representable X; FP64: any d <= 512), which is
 approximate: log-density differences within 2e-3 at N = 10^6, the value itself carries a common offset of ~3e-8 N.
 """
 function logistic(X::AbstractMatrix, y::AbstractVector; prior_sigma=10.0, device=0, tensor_cores=false)
