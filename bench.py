@@ -132,6 +132,8 @@ class ClockSampler:
         self.idx, self.proc, self.path = gpu_index, None, None
 
     def start(self):
+        if os.environ.get("KMC_BENCH_NO_CLOCKS"):   # experiment: is the sampler itself a perturbation?
+            return
         try:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
@@ -140,6 +142,21 @@ class ClockSampler:
                  str(self.idx)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
+
+    def wait_ready(self, timeout=8.0):
+        """Blocks until nvidia-smi has printed its first sample: its start-up (NVML attaches to every GPU of the box) must
+        not overlap the timed region -- measured on 2- and 8-GPU boxes: kernels running during that start-up were 11 %
+        slower (131.6 instead of 118.5 ms per step)."""
+        if not self.proc:
+            return
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < timeout:
+            try:
+                if os.path.getsize(self.path) > 0:
+                    return
+            except OSError:
+                return
+            time.sleep(0.02)
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
@@ -357,9 +374,22 @@ class Env:
         self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     def barrier(self):
+        # synchronize FIRST: a dist.barrier() issued while this rank's kernels are still queued puts NCCL's kernel between
+        # them -- it holds an SM while it waits for the peer, and the next cooperative launch (every SM, all shared memory)
+        # cannot start: measured +12 ms per step on one (random) rank of a 2- or 8-GPU run (profiles/r2_call34.log)
+        self.torch.cuda.synchronize()
         if self.world > 1:
             self.dist.barrier()
-        self.torch.cuda.synchronize()
+            self.torch.cuda.synchronize()
+
+    def gather(self, vals):
+        """vals of every rank, [world][len(vals)]."""
+        if self.world == 1:
+            return [list(vals)]
+        t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
+        out = [self.torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.tolist() for o in out]
 
     def max_sum(self, vals):
         t = self.torch.tensor(vals, dtype=self.torch.float64, device="cuda")
@@ -408,6 +438,7 @@ def run_workload(env, km, workload, steps, warmup, launch_mode=0, tensor_cores=N
     env.barrier()
     clocks = ClockSampler(local)
     clocks.start()
+    clocks.wait_ready()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     env.barrier()
     with torch.cuda.stream(stream):
@@ -458,10 +489,13 @@ def run_workload(env, km, workload, steps, warmup, launch_mode=0, tensor_cores=N
     del x0_pinned, out_th, out_lp, out_ar
     km.lib.kmc_trim()                             # give the cached device blocks back before the next workload
 
+    per_rank = env.gather([statistics.mean(kern_ms), dev_ms / steps, float(clk["sm_mhz"] or 0.0)])
     (dev_ms, e2e_ms, _, _), (_, _, _, launches) = env.max_sum([dev_ms, e2e_s * 1e3, max(kern_ms), float(launches)])
     k_ms = statistics.mean(kern_ms)
     return {
         "wl": wl, "tensor": tensor, "k_ms": k_ms,
+        "per_rank": {"kernel_ms": [round(v[0], 3) for v in per_rank], "ms_per_step": [round(v[1], 3) for v in per_rank],
+                     "sm_mhz": [v[2] for v in per_rank]},
         "value": world * walker_steps_per_step * steps / (dev_ms * 1e-3),
         "ms_per_step": dev_ms / steps,
         "dtype": "bf16x3 split operands, f32 accumulate (tcgen05); f64 state" if tensor else "f64",
@@ -637,6 +671,8 @@ def main():
             "data": "synthetic", "config": r["config"], "roofline": roof, "e2e": r["e2e"],
             "gpu_launches": r["gpu_launches"], "clocks": r["clocks"],
         }
+        if world > 1:
+            line["per_rank"] = r["per_rank"]      # the step time is the slowest rank's: which one, and at what clock
         if others:
             line["others"] = others
         if sharded:
