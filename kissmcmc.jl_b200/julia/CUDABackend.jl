@@ -21,6 +21,8 @@ export LogDensity, exponential, rosenbrock, gaussian, lognormal, logistic, set_o
 using LinearAlgebra: cholesky, Symmetric, diag, inv
 import ..KissMCMC: squash_walkers   # host-side, reused as is (src/samplers.jl:372-428)
 
+# The library name of every `ccall((:sym, LIB[]), ...)` is an expression evaluated at the first call: this needs
+# Julia >= 1.6 (the reference's Project.toml allows 1.2; on older versions make LIB a `const String`).
 const LIB = Ref{String}(get(ENV, "KISSMCMC_CUDA_LIB", "libkissmcmc_cuda"))
 
 const MODE_PHILOX = Int32(0)
