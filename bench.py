@@ -69,7 +69,9 @@ def dominant_kernel(wl, tensor, launch_mode):
             return "tc::gaussian_fused2_kernel" if launch_mode == 0 else \
                 "propose_split_kernel + tc::gaussian_tc_kernel + accept_kernel"
         return "propose_kernel + gaussian_wide_logp_kernel + accept_kernel"
-    if launch_mode == 0 and wl["nw"] * (8 * d + 12) <= 148 * 200 * 1024:
+    # shared-memory-resident state: 2 CTAs per SM, <= 7 rounds of 256 threads per half, 8d + 12 bytes per walker position
+    per_cta = -(-(wl["nw"] // 2) // (2 * 148))
+    if launch_mode == 0 and d <= 4 and per_cta <= 7 * 256 and 2 * per_cta * (8 * d + 12) <= 113 * 1024:
         return "emcee_smem_kernel"
     if launch_mode == 0 and d >= 6 and d % 2 == 0:
         return "emcee_bulk_kernel"
